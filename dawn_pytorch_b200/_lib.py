@@ -1,0 +1,61 @@
+"""ctypes binding of include/dawn_unet.h.  The product path has no fallback: if the CUDA library is
+missing or fails to load, importing this module raises."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdawn_unet.so")
+
+
+class DawnUnetCfg(ctypes.Structure):
+    _fields_ = [("dim", ctypes.c_int), ("n_levels", ctypes.c_int), ("dim_mults", ctypes.c_int * 8),
+                ("channels", ctypes.c_int), ("cond_aud", ctypes.c_int), ("cond_pose", ctypes.c_int),
+                ("cond_eye", ctypes.c_int), ("out_grid_dim", ctypes.c_int), ("out_conf_dim", ctypes.c_int),
+                ("attn_heads", ctypes.c_int), ("attn_dim_head", ctypes.c_int), ("resnet_groups", ctypes.c_int),
+                ("init_kernel_size", ctypes.c_int), ("win_width", ctypes.c_int)]
+
+
+class DawnError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m dawn_pytorch_b200.build` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the DAWN denoising UNet.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i64p, fp, cp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p, ctypes.c_char_p
+    lib.dawn_unet_create.argtypes = [ctypes.POINTER(DawnUnetCfg), ctypes.POINTER(vp)]
+    lib.dawn_unet_destroy.argtypes = [vp]
+    lib.dawn_unet_destroy.restype = None
+    lib.dawn_unet_set_param.argtypes = [vp, cp, fp, i64p, ctypes.c_int]
+    lib.dawn_unet_commit_params.argtypes = [vp]
+    lib.dawn_unet_set_num_frames.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.dawn_unet_set_clip_invariants.argtypes = [vp, fp, fp, vp]
+    lib.dawn_unet_forward.argtypes = [vp, fp, vp, fp, fp, vp]
+    lib.dawn_unet_forward_x3.argtypes = [vp, fp, vp, fp, vp]
+    lib.dawn_unet_forward_host.argtypes = [vp, fp, fp, fp, ctypes.c_int64, fp]
+    lib.dawn_unet_set_tap.argtypes = [vp, cp, fp]
+    lib.dawn_unet_tap_shape.argtypes = [vp, cp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                        ctypes.POINTER(ctypes.c_int)]
+    lib.dawn_unet_last_launch_count.argtypes = [vp]
+    lib.dawn_unet_last_launch_count.restype = ctypes.c_int64
+    lib.dawn_unet_workspace_bytes.argtypes = [vp]
+    lib.dawn_unet_workspace_bytes.restype = ctypes.c_int64
+    lib.dawn_last_error.restype = cp
+    lib.dawn_build_info.restype = cp
+    return lib
+
+
+lib = _load()
+
+EXPORTS = ["dawn_unet_create", "dawn_unet_destroy", "dawn_unet_set_param", "dawn_unet_commit_params",
+           "dawn_unet_set_num_frames", "dawn_unet_set_clip_invariants", "dawn_unet_forward",
+           "dawn_unet_forward_x3", "dawn_unet_forward_host", "dawn_unet_set_tap", "dawn_unet_tap_shape",
+           "dawn_unet_last_launch_count", "dawn_unet_workspace_bytes", "dawn_last_error", "dawn_build_info"]
+
+
+def check(rc, what):
+    if rc != 0:
+        raise DawnError(f"{what} failed (rc={rc}): {lib.dawn_last_error().decode()}")

@@ -1,0 +1,54 @@
+// Universal implicit-GEMM for the channels-last (F,H,W,C) activations of the DAWN UNet.
+//   Out[m, n] = epilogue( sum_{tap, c} A[pixel(m, tap), c] * B[tap*Cin + c, n] )
+// rows m enumerate (frame, i, j) over an output sub-grid; `taps` give the input offsets, so the
+// same kernel serves 3x3 / 7x7 convs, 4x4 stride-2 down convs, the 4 parity classes of the 4x4
+// stride-2 transposed conv, 1x1 convs and Linear layers (reference U:165-176, 229, 417, 608-609, 662-663).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace dawn {
+
+enum Epi : int {
+  EPI_PLAIN = 0,         // acc + bias (+ residual), optional GroupNorm partial statistics
+  EPI_QKV_TEMPORAL = 1,  // LayerNorm fold + rotary on q,k            (U:179-188, 673-693)
+  EPI_QKV_SLA = 2,       // LayerNorm fold + softmax over head dim of q, * d^-0.5   (U:615-621)
+  EPI_QKV_MID = 3,       // LayerNorm fold only                        (U:841-843)
+  EPI_CA_GATE = 4,       // LayerNorm_img fold + cosine-sim 2-key softmax -> gate  (U:519-555)
+  EPI_GN_APPLY = 5,      // Out = SiLU(FiLM(GroupNorm(Y))) + acc       (U:235-248, 473-476)
+};
+
+struct GemmParams {
+  // A operand (gathered)
+  const float* A; int lda; int Cin;
+  int IH, IW;              // input frame dims
+  int OHs, OWs;            // output sub-grid dims; rows m = (f, i, j)
+  int in_stride;           // input pixel = (i*in_stride + dy, j*in_stride + dx)
+  int ntaps; signed char dy[52]; signed char dx[52];
+  int M, N, K;             // K = ntaps * Cin (multiple of 32)
+  int rows_per_batch;      // rows sharing one B matrix (P for per-frame weights, else M)
+  // B operand [K][ldb] (ldb multiple of 64, zero padded)
+  const float* B; int ldb; long long b_batch_stride;
+  // output
+  float* Out; int ldo; int OH, OW, out_stride, oy0, ox0;
+  const float* bias;
+  const float* Res; int ldr;
+  double* stats; int cpg;  // GroupNorm accumulators [groups][2], channels per group
+  // LayerNorm fold
+  const float* rowstats;   // [M][2] (mu, rstd)
+  const float* wsum;       // [N]  sum_k B[k][n]
+  const float* rot;        // [F][16][2] (cos, sin)
+  int P;                   // positions per frame (row -> frame index)
+  float q_post_scale;
+  // cross-attention gate
+  const float* kq;         // [F][3][64]
+  const float* nkq;        // [3][8]
+  float* gates;            // [M][24]
+  // GroupNorm apply
+  const float* Y; int ldy; const double* gn_stats; const float* gn_w; const float* gn_b;
+  const float* film;       // [2N] scale | shift, or null
+  double gn_count;         // elements per group
+};
+
+int launch_gemm(const GemmParams& p, int epi, cudaStream_t st);
+
+}  // namespace dawn

@@ -1,0 +1,940 @@
+// Host-side orchestration + C-ABI of the DAWN denoising UNet (reference U:728-965; see include/dawn_unet.h).
+// One handle = one GPU = one clip at a time.  Weights are repacked once into GEMM-friendly layouts;
+// activations live channels-last (F, H, W, C) in a workspace sized by dawn_unet_set_num_frames.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/dawn_unet.h"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace dawn {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+
+#define DAWN_CHECK(cond, msg)                 \
+  do {                                        \
+    if (!(cond)) {                            \
+      ::dawn::set_last_error(msg);            \
+      return -1;                              \
+    }                                         \
+  } while (0)
+#define DAWN_TRY(expr)           \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != 0) return _rc;    \
+  } while (0)
+
+struct HostParam {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+  int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
+};
+
+struct Act {          // channels-last activation view: pixel stride ld, C channels, frame size H x W
+  float* p = nullptr; int ld = 0; int C = 0; int H = 0; int W = 0;
+};
+
+struct ConvW { float* w = nullptr; float* b = nullptr; int K = 0, N = 0, ldb = 0; };
+
+struct CrossAttnW { float *Wkv, *nkv, *qs, *ks, *Wout, *gout; };
+
+struct ResBlockW {
+  std::string name;
+  int ci = 0, co = 0;
+  bool cond = false, res = false;
+  ConvW c1, c2, cres;
+  float *gn1w = nullptr, *gn1b = nullptr, *gn2w = nullptr, *gn2b = nullptr;
+  float *tW = nullptr, *tB = nullptr;
+  float *mW[3] = {nullptr, nullptr, nullptr}, *mB[3] = {nullptr, nullptr, nullptr};   // pose, aud, eye MLPs
+  float *Wq = nullptr, *wsumq = nullptr;                                                 // [ci][192], [192]
+  CrossAttnW ca[3];
+  // per-clip (depend on F / cond)
+  float *film = nullptr, *kq = nullptr, *nkq = nullptr, *T = nullptr, *G = nullptr;
+  int ldbT = 0;
+  int st1 = 0, st2 = 0;
+};
+
+struct AttnW {     // temporal attention / mid spatial attention (U:648-725)
+  int C = 0; float *Wqkv = nullptr, *wsum = nullptr; ConvW out;
+};
+struct SlaW {      // spatial linear attention (U:602-627)
+  int C = 0; float *Wqkv = nullptr, *wsum = nullptr, *WoutT = nullptr, *bout = nullptr;
+};
+struct UpW { ConvW cls[4]; };
+
+}  // namespace dawn
+
+using namespace dawn;
+
+struct dawn_unet {
+  dawn_unet_cfg cfg{};
+  int nlev = 0;
+  std::vector<int> dims;                       // [dim, dim*m0, ...]
+  std::vector<std::pair<int, int>> in_out;
+  int cond_dim = 0, tdim = 0;
+  std::unordered_map<std::string, HostParam> raw;
+  bool committed = false;
+
+  // packed weights
+  std::vector<void*> owned;                    // weight allocations
+  std::vector<void*> ws_owned;                 // workspace allocations
+  int64_t ws_bytes = 0;
+  ConvW init_full;                             // 7x7 over channels padded to cin_pad
+  float* init_w3 = nullptr;                    // [k*k*3][dim] for the 3 noisy channels
+  int cin_pad = 0;
+  float *time_freqs = nullptr, *tW1 = nullptr, *tb1 = nullptr, *tW2 = nullptr, *tb2 = nullptr;
+  float *rel_bias = nullptr, *rot_freqs = nullptr;
+  std::vector<ResBlockW> rb;                   // all resnet blocks
+  std::map<std::string, int> rb_index;
+  AttnW init_ta, mid_sa, mid_ta;
+  std::vector<AttnW> down_ta, up_ta;
+  std::vector<SlaW> down_sla, up_sla;
+  std::vector<ConvW> down_conv;
+  std::vector<UpW> up_conv;
+  float *headW[2] = {nullptr, nullptr}, *headB[2] = {nullptr, nullptr};
+  FilmDesc* film_descs = nullptr; int n_film = 0;
+
+  // workspace (per set_num_frames)
+  int F = 0, H = 0, W = 0;
+  std::vector<int> lH, lW;
+  float *X288 = nullptr, *FEA288 = nullptr, *MAP = nullptr, *XR = nullptr, *S0 = nullptr;
+  std::vector<float*> bufA, bufB, CAT, DS;
+  float *Y = nullptr, *A1 = nullptr, *QKV = nullptr, *O = nullptr, *ROWSTATS = nullptr, *GATES = nullptr, *WT = nullptr;
+  float *BF = nullptr, *HF = nullptr, *HO = nullptr, *ROT = nullptr, *TSILU = nullptr, *CTX = nullptr, *KV = nullptr;
+  double* STATS = nullptr; int n_stats = 0;
+  int64_t* T_HOSTSIDE = nullptr;               // device int64 for forward_host
+  float *H_XT = nullptr, *H_FEA = nullptr, *H_COND = nullptr, *H_OUT = nullptr;   // device staging for forward_host
+  bool have_invariants = false;
+
+  std::map<std::string, float*> taps;
+  int64_t launches = 0;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ allocation helpers
+int dev_alloc(std::vector<void*>& owner, size_t nfloats, float** out, int64_t* counter = nullptr) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(nfloats, 4) * sizeof(float);
+  DAWN_CUDA_OK(cudaMalloc(&p, bytes));
+  owner.push_back(p);
+  if (counter) *counter += (int64_t)bytes;
+  *out = (float*)p;
+  return 0;
+}
+int dev_upload(dawn_unet* h, const std::vector<float>& v, float** out) {
+  DAWN_TRY(dev_alloc(h->owned, v.size(), out));
+  DAWN_CUDA_OK(cudaMemcpy(*out, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+void free_all(std::vector<void*>& v) {
+  for (void* p : v) cudaFree(p);
+  v.clear();
+}
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+const HostParam* find(dawn_unet* h, const std::string& name) {
+  auto it = h->raw.find(name);
+  return it == h->raw.end() ? nullptr : &it->second;
+}
+int need(dawn_unet* h, const std::string& name, std::vector<int64_t> shape, const HostParam** out) {
+  const HostParam* p = find(h, name);
+  if (!p) { set_last_error("missing parameter: " + name); return -1; }
+  if (p->shape != shape) {
+    std::string s = "parameter " + name + " has shape (";
+    for (auto d : p->shape) s += std::to_string(d) + ",";
+    s += ") expected (";
+    for (auto d : shape) s += std::to_string(d) + ",";
+    set_last_error(s + ")");
+    return -1;
+  }
+  *out = p;
+  return 0;
+}
+
+// conv weight (co, ci, 1, kh, kw) -> [ (ky*kw+kx)*ci_pad + c ][ldb]
+int pack_conv(dawn_unet* h, const std::string& prefix, int co, int ci, int kh, int kw, int ci_pad, bool bias, ConvW* out) {
+  const HostParam* w; const HostParam* b = nullptr;
+  DAWN_TRY(need(h, prefix + ".weight", {co, ci, 1, kh, kw}, &w));
+  if (bias) DAWN_TRY(need(h, prefix + ".bias", {co}, &b));
+  const int ldb = round_up(co, 64);
+  const int K = kh * kw * ci_pad;
+  std::vector<float> m((size_t)K * ldb, 0.f);
+  for (int n = 0; n < co; ++n)
+    for (int c = 0; c < ci; ++c)
+      for (int t = 0; t < kh * kw; ++t)
+        m[((size_t)t * ci_pad + c) * ldb + n] = w->data[((size_t)n * ci + c) * kh * kw + t];
+  DAWN_TRY(dev_upload(h, m, &out->w));
+  out->b = nullptr;
+  if (bias) {
+    std::vector<float> bb(ldb, 0.f);
+    std::copy(b->data.begin(), b->data.end(), bb.begin());
+    DAWN_TRY(dev_upload(h, bb, &out->b));
+  }
+  out->K = K; out->N = co; out->ldb = ldb;
+  return 0;
+}
+
+// Linear weight (N, K) [+ optional per-input gain, + per-output-row scale for the first `nscale` rows]
+// -> [K][ldb], plus column sums for the LayerNorm fold
+int pack_linear(dawn_unet* h, const HostParam* w, int N, int K, const float* gain, float qscale, int nscale,
+                float** Wout, float** wsum, int* ldb_out) {
+  const int ldb = round_up(N, 64);
+  std::vector<float> m((size_t)K * ldb, 0.f), s(ldb, 0.f);
+  for (int n = 0; n < N; ++n) {
+    double acc = 0.0;
+    const float sc = (n < nscale) ? qscale : 1.0f;
+    for (int k = 0; k < K; ++k) {
+      float v = w->data[(size_t)n * K + k];
+      if (gain) v *= gain[k];
+      v *= sc;
+      m[(size_t)k * ldb + n] = v;
+      acc += v;
+    }
+    s[n] = (float)acc;
+  }
+  DAWN_TRY(dev_upload(h, m, Wout));
+  if (wsum) DAWN_TRY(dev_upload(h, s, wsum));
+  if (ldb_out) *ldb_out = ldb;
+  return 0;
+}
+
+int upload_raw(dawn_unet* h, const std::string& name, std::vector<int64_t> shape, float** out) {
+  const HostParam* p;
+  DAWN_TRY(need(h, name, shape, &p));
+  return dev_upload(h, p->data, out);
+}
+
+int pack_resblock(dawn_unet* h, const std::string& name, int ci, int co, bool cond, int* stat_counter) {
+  ResBlockW r;
+  r.name = name; r.ci = ci; r.co = co; r.cond = cond; r.res = (ci != co);
+  DAWN_CHECK(ci % 32 == 0 && co % 64 == 0, "channel counts must be multiples of 64 (dim=64 family)");
+  DAWN_TRY(pack_conv(h, name + ".block1.proj", co, ci, 3, 3, ci, true, &r.c1));
+  DAWN_TRY(pack_conv(h, name + ".block2.proj", co, co, 3, 3, co, true, &r.c2));
+  DAWN_TRY(upload_raw(h, name + ".block1.norm.weight", {co}, &r.gn1w));
+  DAWN_TRY(upload_raw(h, name + ".block1.norm.bias", {co}, &r.gn1b));
+  DAWN_TRY(upload_raw(h, name + ".block2.norm.weight", {co}, &r.gn2w));
+  DAWN_TRY(upload_raw(h, name + ".block2.norm.bias", {co}, &r.gn2b));
+  if (r.res) DAWN_TRY(pack_conv(h, name + ".res_conv", co, ci, 1, 1, ci, true, &r.cres));
+  r.st1 = (*stat_counter)++;
+  r.st2 = (*stat_counter)++;
+  if (cond) {
+    const int tdim = h->tdim;
+    DAWN_TRY(upload_raw(h, name + ".time_mlp.1.weight", {2 * co, tdim}, &r.tW));
+    DAWN_TRY(upload_raw(h, name + ".time_mlp.1.bias", {2 * co}, &r.tB));
+    const char* mlp[3] = {"pose_mlp", "audio_mlp", "eye_mlp"};
+    const int kdim[3] = {h->cfg.cond_pose, h->cfg.cond_aud, h->cfg.cond_eye};
+    const char* can[3] = {"cross_attn_pose", "cross_attn_aud", "cross_attn_eye"};
+    std::vector<float> wq((size_t)ci * 192, 0.f), wsum(192, 0.f);
+    for (int a = 0; a < 3; ++a) {
+      DAWN_TRY(upload_raw(h, name + "." + mlp[a] + ".1.weight", {2 * co, kdim[a]}, &r.mW[a]));
+      DAWN_TRY(upload_raw(h, name + "." + mlp[a] + ".1.bias", {2 * co}, &r.mB[a]));
+      const std::string p = name + "." + can[a];
+      const HostParam *g, *q;
+      DAWN_TRY(need(h, p + ".norm.g", {ci}, &g));
+      DAWN_TRY(need(h, p + ".to_q.weight", {64, ci}, &q));
+      for (int j = 0; j < 64; ++j) {
+        double acc = 0.0;
+        for (int k = 0; k < ci; ++k) {
+          const float v = q->data[(size_t)j * ci + k] * g->data[k];     // LayerNorm_img gain folded (U:203, 519)
+          wq[(size_t)k * 192 + a * 64 + j] = v;
+          acc += v;
+        }
+        wsum[a * 64 + j] = (float)acc;
+      }
+      DAWN_TRY(upload_raw(h, p + ".to_kv.weight", {128, 2 * co}, &r.ca[a].Wkv));
+      DAWN_TRY(upload_raw(h, p + ".null_kv", {2, 8}, &r.ca[a].nkv));
+      DAWN_TRY(upload_raw(h, p + ".q_scale", {8}, &r.ca[a].qs));
+      DAWN_TRY(upload_raw(h, p + ".k_scale", {8}, &r.ca[a].ks));
+      DAWN_TRY(upload_raw(h, p + ".to_out.0.weight", {co, 64}, &r.ca[a].Wout));
+      DAWN_TRY(upload_raw(h, p + ".to_out.1.g", {co}, &r.ca[a].gout));
+    }
+    DAWN_TRY(dev_upload(h, wq, &r.Wq));
+    DAWN_TRY(dev_upload(h, wsum, &r.wsumq));
+  }
+  h->rb_index[name] = (int)h->rb.size();
+  h->rb.push_back(r);
+  return 0;
+}
+
+int pack_attn(dawn_unet* h, const std::string& norm_name, const std::string& fn, int C, AttnW* a) {
+  const HostParam *g, *qkv, *o;
+  DAWN_TRY(need(h, norm_name + ".gamma", {1, C, 1, 1, 1}, &g));
+  DAWN_TRY(need(h, fn + ".to_qkv.weight", {768, C}, &qkv));
+  DAWN_TRY(need(h, fn + ".to_out.weight", {C, 256}, &o));
+  a->C = C;
+  const float scale = 1.0f / sqrtf(32.0f);                                   // q * dim_head^-0.5 (U:657, 687)
+  DAWN_TRY(pack_linear(h, qkv, 768, C, g->data.data(), scale, 256, &a->Wqkv, &a->wsum, nullptr));
+  int ldb = 0;
+  DAWN_TRY(pack_linear(h, o, C, 256, nullptr, 1.f, 0, &a->out.w, nullptr, &ldb));
+  a->out.b = nullptr; a->out.K = 256; a->out.N = C; a->out.ldb = ldb;
+  return 0;
+}
+
+int pack_sla(dawn_unet* h, const std::string& p, int C, SlaW* s) {        // p = "downs.L.2.fn"
+  const HostParam *g, *qkv, *o, *b;
+  DAWN_TRY(need(h, p + ".norm.gamma", {1, C, 1, 1, 1}, &g));
+  DAWN_TRY(need(h, p + ".fn.to_qkv.weight", {768, C, 1, 1}, &qkv));
+  DAWN_TRY(need(h, p + ".fn.to_out.weight", {C, 256, 1, 1}, &o));
+  DAWN_TRY(need(h, p + ".fn.to_out.bias", {C}, &b));
+  s->C = C;
+  DAWN_TRY(pack_linear(h, qkv, 768, C, g->data.data(), 1.f, 0, &s->Wqkv, &s->wsum, nullptr));
+  std::vector<float> wt((size_t)256 * C);
+  for (int c = 0; c < C; ++c)
+    for (int k = 0; k < 256; ++k) wt[(size_t)k * C + c] = o->data[(size_t)c * 256 + k];
+  DAWN_TRY(dev_upload(h, wt, &s->WoutT));
+  std::vector<float> bb(round_up(C, 64), 0.f);
+  std::copy(b->data.begin(), b->data.end(), bb.begin());
+  DAWN_TRY(dev_upload(h, bb, &s->bout));
+  return 0;
+}
+
+// ConvTranspose3d (1,4,4)/(1,2,2)/(0,1,1) weight (ci, co, 1, 4, 4): four output-parity classes, each a 2x2 conv.
+// out[y] gets in[(y+1-ky)/2]: y even -> ky in {1 (dy 0), 3 (dy -1)}; y odd -> ky in {0 (dy +1), 2 (dy 0)}.   (U:165-167)
+static const int kUpK[2][2] = {{1, 3}, {0, 2}};
+static const int kUpD[2][2] = {{0, -1}, {1, 0}};
+int pack_up(dawn_unet* h, const std::string& name, int C, UpW* u) {
+  const HostParam *w, *b;
+  DAWN_TRY(need(h, name + ".weight", {C, C, 1, 4, 4}, &w));
+  DAWN_TRY(need(h, name + ".bias", {C}, &b));
+  const int ldb = round_up(C, 64);
+  std::vector<float> bb(ldb, 0.f);
+  std::copy(b->data.begin(), b->data.end(), bb.begin());
+  float* bdev;
+  DAWN_TRY(dev_upload(h, bb, &bdev));
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      std::vector<float> m((size_t)4 * C * ldb, 0.f);
+      for (int ty = 0; ty < 2; ++ty)
+        for (int tx = 0; tx < 2; ++tx) {
+          const int ky = kUpK[py][ty], kx = kUpK[px][tx];
+          for (int c = 0; c < C; ++c)
+            for (int n = 0; n < C; ++n)
+              m[((size_t)(ty * 2 + tx) * C + c) * ldb + n] = w->data[(((size_t)c * C + n) * 4 + ky) * 4 + kx];
+        }
+      ConvW& cw = u->cls[py * 2 + px];
+      DAWN_TRY(dev_upload(h, m, &cw.w));
+      cw.b = bdev; cw.K = 4 * C; cw.N = C; cw.ldb = ldb;
+    }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ GEMM wrappers
+void base_params(GemmParams& p, const Act& in, int F) {
+  memset(&p, 0, sizeof(p));
+  p.A = in.p; p.lda = in.ld; p.Cin = in.C;
+  p.IH = in.H; p.IW = in.W; p.OHs = in.H; p.OWs = in.W; p.in_stride = 1;
+  p.ntaps = 1; p.dy[0] = 0; p.dx[0] = 0;
+  p.M = F * in.H * in.W; p.rows_per_batch = p.M;
+  p.OH = in.H; p.OW = in.W; p.out_stride = 1; p.oy0 = 0; p.ox0 = 0;
+  p.P = in.H * in.W;
+  p.q_post_scale = 1.f;
+}
+void set_weights(GemmParams& p, const ConvW& w) {
+  p.B = w.w; p.ldb = w.ldb; p.b_batch_stride = 0; p.N = w.N; p.K = w.K; p.bias = w.b;
+}
+void set_square_taps(GemmParams& p, int k, int pad) {
+  p.ntaps = k * k;
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx) { p.dy[ky * k + kx] = (signed char)(ky - pad); p.dx[ky * k + kx] = (signed char)(kx - pad); }
+}
+
+struct Ctx {
+  dawn_unet* h; cudaStream_t st;
+  int gemm(const GemmParams& p, int epi) { h->launches++; return launch_gemm(p, epi, st); }
+};
+
+int tap(Ctx& c, const std::string& name, const Act& a);
+
+// conv k x k, stride 1, same padding, + bias, optional GroupNorm statistics slot
+int conv_same(Ctx& c, const Act& in, const ConvW& w, int k, const Act& out, int stat_slot) {
+  GemmParams p; base_params(p, in, c.h->F);
+  set_weights(p, w); set_square_taps(p, k, k / 2);
+  p.Out = out.p; p.ldo = out.ld;
+  if (stat_slot >= 0) { p.stats = c.h->STATS + 16 * stat_slot; p.cpg = w.N / 8; }
+  return c.gemm(p, EPI_PLAIN);
+}
+
+// ResnetBlock_ca_mul (U:363-479)
+int resblock(Ctx& c, const ResBlockW& r, const Act& x, const Act& out) {
+  dawn_unet* h = c.h;
+  const int F = h->F, M = F * x.H * x.W, P = x.H * x.W;
+  DAWN_CHECK(x.C == r.ci && out.C == r.co, "resblock channel mismatch: " + r.name);
+  Act y{h->Y, r.co, r.co, x.H, x.W}, a1{h->A1, r.co, r.co, x.H, x.W};
+  const double count = (double)M * (r.co / 8);
+  if (r.cond) {
+    // cross-attention gates from the raw block input (U:454-463): LayerNorm_img folded into the q projection
+    h->launches++;
+    DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
+    GemmParams p; base_params(p, x, F);
+    p.B = r.Wq; p.ldb = 192; p.N = 192; p.K = r.ci;
+    p.rowstats = h->ROWSTATS; p.wsum = r.wsumq; p.kq = r.kq; p.nkq = r.nkq; p.gates = h->GATES;
+    DAWN_TRY(c.gemm(p, EPI_CA_GATE));
+    h->launches++;
+    DAWN_TRY(launch_ca_rstd(h->GATES, r.G, M, P, h->WT, c.st));
+  }
+  DAWN_TRY(conv_same(c, x, r.c1, 3, y, r.st1));
+  if (r.cond) {
+    // a1 = SiLU(FiLM(GN(y))) + h_cond, h_cond = Wt (M x 32) @ T_f (32 x co) per frame
+    Act wt{h->WT, 32, 32, x.H, x.W};
+    GemmParams p; base_params(p, wt, F);
+    p.B = r.T; p.ldb = r.ldbT; p.b_batch_stride = (long long)32 * r.ldbT; p.N = r.co; p.K = 32;
+    p.rows_per_batch = P;
+    p.Out = a1.p; p.ldo = a1.ld;
+    p.Y = y.p; p.ldy = y.ld; p.gn_stats = h->STATS + 16 * r.st1; p.gn_w = r.gn1w; p.gn_b = r.gn1b;
+    p.film = r.film; p.gn_count = count; p.cpg = r.co / 8;
+    DAWN_TRY(c.gemm(p, EPI_GN_APPLY));
+  } else {
+    h->launches++;
+    DAWN_TRY(launch_gn_apply(y.p, y.ld, r.co, M, h->STATS + 16 * r.st1, count, r.co / 8, r.gn1w, r.gn1b, nullptr,
+                             nullptr, 0, a1.p, a1.ld, c.st));
+  }
+  DAWN_TRY(conv_same(c, a1, r.c2, 3, y, r.st2));
+  const float* res = x.p; int ldr = x.ld;
+  if (r.res) {
+    GemmParams p; base_params(p, x, F);
+    set_weights(p, r.cres);
+    p.Out = out.p; p.ldo = out.ld;
+    DAWN_TRY(c.gemm(p, EPI_PLAIN));
+    res = out.p; ldr = out.ld;
+  }
+  h->launches++;
+  DAWN_TRY(launch_gn_apply(y.p, y.ld, r.co, M, h->STATS + 16 * r.st2, count, r.co / 8, r.gn2w, r.gn2b, nullptr,
+                           res, ldr, out.p, out.ld, c.st));
+  return tap(c, r.name, out);
+}
+
+// Residual(PreNorm(temporal Attention)) (U:648-725 / LA:275-342): x -> dst = x + to_out(attn(...))
+int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const std::string& name) {
+  dawn_unet* h = c.h;
+  const int F = h->F, P = x.H * x.W, M = F * P;
+  h->launches++;
+  DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
+  {
+    GemmParams p; base_params(p, x, F);
+    p.B = w.Wqkv; p.ldb = 768; p.N = 768; p.K = x.C;
+    p.rowstats = h->ROWSTATS; p.wsum = w.wsum; p.rot = h->ROT;
+    p.Out = h->QKV; p.ldo = 768;
+    DAWN_TRY(c.gemm(p, EPI_QKV_TEMPORAL));
+  }
+  {
+    AttnArgs a{};
+    a.qkv = h->QKV; a.ld = 768; a.out = h->O; a.ldo = 256;
+    a.nseq = P; a.L = F; a.seq_base_stride = 1; a.elem_stride = P;
+    a.band = h->cfg.win_width; a.bias = h->rel_bias; a.q_lo = 0; a.q_hi = F;
+    h->launches++;
+    DAWN_TRY(launch_attention(a, c.st));
+  }
+  {
+    Act o{h->O, 256, 256, x.H, x.W};
+    GemmParams p; base_params(p, o, F);
+    set_weights(p, w.out);
+    p.Res = x.p; p.ldr = x.ld; p.Out = dst.p; p.ldo = dst.ld;
+    DAWN_TRY(c.gemm(p, EPI_PLAIN));
+  }
+  return tap(c, name, dst);
+}
+
+// Residual(PreNorm(Attention over the h*w tokens of each frame)) (U:841-843), in place
+int mid_spatial_attn(Ctx& c, const AttnW& w, const Act& x, const std::string& name) {
+  dawn_unet* h = c.h;
+  const int F = h->F, P = x.H * x.W, M = F * P;
+  h->launches++;
+  DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
+  {
+    GemmParams p; base_params(p, x, F);
+    p.B = w.Wqkv; p.ldb = 768; p.N = 768; p.K = x.C;
+    p.rowstats = h->ROWSTATS; p.wsum = w.wsum;
+    p.Out = h->QKV; p.ldo = 768;
+    DAWN_TRY(c.gemm(p, EPI_QKV_MID));
+  }
+  {
+    AttnArgs a{};
+    a.qkv = h->QKV; a.ld = 768; a.out = h->O; a.ldo = 256;
+    a.nseq = F; a.L = P; a.seq_base_stride = P; a.elem_stride = 1;
+    a.band = 1 << 30; a.bias = nullptr; a.q_lo = 0; a.q_hi = P;
+    h->launches++;
+    DAWN_TRY(launch_attention(a, c.st));
+  }
+  {
+    Act o{h->O, 256, 256, x.H, x.W};
+    GemmParams p; base_params(p, o, F);
+    set_weights(p, w.out);
+    p.Res = x.p; p.ldr = x.ld; p.Out = x.p; p.ldo = x.ld;
+    DAWN_TRY(c.gemm(p, EPI_PLAIN));
+  }
+  return tap(c, name, x);
+}
+
+// Residual(PreNorm(SpatialLinearAttention)) (U:602-627), in place
+int sla(Ctx& c, const SlaW& w, const Act& x, const std::string& name) {
+  dawn_unet* h = c.h;
+  const int F = h->F, P = x.H * x.W, M = F * P;
+  h->launches++;
+  DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
+  {
+    GemmParams p; base_params(p, x, F);
+    p.B = w.Wqkv; p.ldb = 768; p.N = 768; p.K = x.C;
+    p.rowstats = h->ROWSTATS; p.wsum = w.wsum; p.q_post_scale = 1.0f / sqrtf(32.0f);
+    p.Out = h->QKV; p.ldo = 768;
+    DAWN_TRY(c.gemm(p, EPI_QKV_SLA));
+  }
+  const int ldb = round_up(x.C, 64);
+  h->launches++;
+  DAWN_TRY(launch_sla_context(h->QKV, 768, F, P, w.WoutT, x.C, h->BF, ldb, c.st));
+  {
+    Act q{h->QKV, 768, 256, x.H, x.W};
+    GemmParams p; base_params(p, q, F);
+    p.B = h->BF; p.ldb = ldb; p.b_batch_stride = (long long)256 * ldb; p.N = x.C; p.K = 256;
+    p.rows_per_batch = P; p.bias = w.bout;
+    p.Res = x.p; p.ldr = x.ld; p.Out = x.p; p.ldo = x.ld;
+    DAWN_TRY(c.gemm(p, EPI_PLAIN));
+  }
+  return tap(c, name, x);
+}
+
+int downsample(Ctx& c, const ConvW& w, const Act& x, const Act& out, const std::string& name) {   // U:175-176
+  GemmParams p; base_params(p, x, c.h->F);
+  set_weights(p, w);
+  p.OHs = out.H; p.OWs = out.W; p.in_stride = 2;
+  p.ntaps = 16;
+  for (int ky = 0; ky < 4; ++ky)
+    for (int kx = 0; kx < 4; ++kx) { p.dy[ky * 4 + kx] = (signed char)(ky - 1); p.dx[ky * 4 + kx] = (signed char)(kx - 1); }
+  p.M = c.h->F * out.H * out.W; p.rows_per_batch = p.M;
+  p.OH = out.H; p.OW = out.W; p.P = out.H * out.W;
+  p.Out = out.p; p.ldo = out.ld;
+  DAWN_TRY(c.gemm(p, EPI_PLAIN));
+  return tap(c, name, out);
+}
+
+int upsample(Ctx& c, const UpW& u, const Act& x, const Act& out, const std::string& name) {       // U:165-167
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      GemmParams p; base_params(p, x, c.h->F);
+      set_weights(p, u.cls[py * 2 + px]);
+      p.ntaps = 4;
+      for (int ty = 0; ty < 2; ++ty)
+        for (int tx = 0; tx < 2; ++tx) { p.dy[ty * 2 + tx] = (signed char)kUpD[py][ty]; p.dx[ty * 2 + tx] = (signed char)kUpD[px][tx]; }
+      p.OH = out.H; p.OW = out.W; p.out_stride = 2; p.oy0 = py; p.ox0 = px;
+      p.Out = out.p; p.ldo = out.ld;
+      DAWN_TRY(c.gemm(p, EPI_PLAIN));
+    }
+  return tap(c, name, out);
+}
+
+// (F, P, C) channels-last -> (C, F, P) for taps
+__global__ void nhwc_to_ncf_kernel(const float* __restrict__ x, int ld, int C, long long M, float* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * C) return;
+  const long long m = idx / C; const int ch = (int)(idx - m * C);
+  out[(size_t)ch * M + m] = x[(size_t)m * ld + ch];
+}
+int tap(Ctx& c, const std::string& name, const Act& a) {
+  auto it = c.h->taps.find(name);
+  if (it == c.h->taps.end() || it->second == nullptr) return 0;
+  const long long M = (long long)c.h->F * a.H * a.W;
+  nhwc_to_ncf_kernel<<<(int)((M * a.C + 255) / 256), 256, 0, c.st>>>(a.p, a.ld, a.C, M, it->second);
+  DAWN_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ per-clip tables
+int prep_cond(dawn_unet* h, const float* cond, cudaStream_t st) {
+  const int F = h->F;
+  const int off[3] = {h->cfg.cond_aud, 0, h->cfg.cond_aud + h->cfg.cond_pose};          // pose, aud, eye slices (U:425-428)
+  const int kd[3] = {h->cfg.cond_pose, h->cfg.cond_aud, h->cfg.cond_eye};
+  for (auto& r : h->rb) {
+    if (!r.cond) continue;
+    for (int a = 0; a < 3; ++a) {
+      h->launches += 3;
+      DAWN_TRY(launch_cond_mlp(cond, h->cond_dim, off[a], kd[a], r.mW[a], r.mB[a], 2 * r.co, F, h->CTX, st));
+      DAWN_TRY(launch_linear_nobias(h->CTX, 2 * r.co, r.ca[a].Wkv, 128, F, h->KV, st));
+      CaTableArgs t{};
+      t.kv = h->KV; t.nkv = r.ca[a].nkv; t.qs = r.ca[a].qs; t.ks = r.ca[a].ks; t.Wout = r.ca[a].Wout; t.gout = r.ca[a].gout;
+      t.co = r.co; t.ldbT = r.ldbT; t.ca = a; t.kq = r.kq; t.nkq = r.nkq; t.T = r.T; t.G = r.G;
+      DAWN_TRY(launch_ca_tables(t, F, st));
+    }
+  }
+  return 0;
+}
+
+int forward_core(dawn_unet* h, const int64_t* t_dev, float* out, cudaStream_t st) {
+  Ctx c{h, st};
+  const int F = h->F, nlev = h->nlev, dim = h->cfg.dim;
+  DAWN_CUDA_OK(cudaMemsetAsync(h->STATS, 0, sizeof(double) * 16 * h->n_stats, st));
+  h->launches += 2;
+  DAWN_TRY(launch_time_mlp(t_dev, h->time_freqs, dim, h->tW1, h->tb1, h->tW2, h->tb2, h->TSILU, st));
+  DAWN_TRY(launch_film(h->film_descs, h->n_film, h->TSILU, h->tdim, st));
+
+  const int H0 = h->lH[0], W0 = h->lW[0];
+  Act r{h->XR + dim, 2 * dim, dim, H0, W0};            // init conv output lives in the second half of cat(x, r) (U:911, 955)
+  DAWN_TRY(tap(c, "init_conv", r));
+  Act s0{h->S0, dim, dim, H0, W0};
+  DAWN_TRY(temporal_attn(c, h->init_ta, r, s0, "init_temporal_attn"));
+
+  Act x = s0;
+  for (int L = 0; L < nlev; ++L) {
+    const int co = h->in_out[L].second;
+    Act a{h->bufA[L], co, co, h->lH[L], h->lW[L]}, b{h->bufB[L], co, co, h->lH[L], h->lW[L]};
+    Act skip{h->CAT[L] + co, 2 * co, co, h->lH[L], h->lW[L]};
+    const std::string pre = "downs." + std::to_string(L);
+    DAWN_TRY(resblock(c, h->rb[h->rb_index[pre + ".0"]], x, a));
+    DAWN_TRY(resblock(c, h->rb[h->rb_index[pre + ".1"]], a, b));
+    DAWN_TRY(sla(c, h->down_sla[L], b, pre + ".2"));
+    DAWN_TRY(temporal_attn(c, h->down_ta[L], b, skip, pre + ".3"));
+    if (L < nlev - 1) {
+      Act d{h->DS[L + 1], co, co, h->lH[L + 1], h->lW[L + 1]};
+      DAWN_TRY(downsample(c, h->down_conv[L], skip, d, pre + ".4"));
+      x = d;
+    } else {
+      x = skip;
+    }
+  }
+  {
+    const int L = nlev - 1, cm = h->in_out[L].second;
+    Act a{h->bufA[L], cm, cm, h->lH[L], h->lW[L]};
+    Act xfirst{h->CAT[L], 2 * cm, cm, h->lH[L], h->lW[L]};
+    DAWN_TRY(resblock(c, h->rb[h->rb_index["mid_block1"]], x, a));
+    DAWN_TRY(mid_spatial_attn(c, h->mid_sa, a, "mid_spatial_attn"));
+    DAWN_TRY(temporal_attn(c, h->mid_ta, a, a, "mid_temporal_attn"));
+    DAWN_TRY(resblock(c, h->rb[h->rb_index["mid_block2"]], a, xfirst));
+  }
+  for (int K = 0; K < nlev; ++K) {
+    const int l = nlev - 1 - K;
+    const int ci = h->in_out[l].first, co = h->in_out[l].second;
+    Act cat{h->CAT[l], 2 * co, 2 * co, h->lH[l], h->lW[l]};
+    Act a{h->bufA[l], ci, ci, h->lH[l], h->lW[l]}, b{h->bufB[l], ci, ci, h->lH[l], h->lW[l]};
+    const std::string pre = "ups." + std::to_string(K);
+    DAWN_TRY(resblock(c, h->rb[h->rb_index[pre + ".0"]], cat, a));
+    DAWN_TRY(resblock(c, h->rb[h->rb_index[pre + ".1"]], a, b));
+    DAWN_TRY(sla(c, h->up_sla[K], b, pre + ".2"));
+    if (K < nlev - 1) {
+      DAWN_TRY(temporal_attn(c, h->up_ta[K], b, b, pre + ".3"));
+      const int cn = h->in_out[l - 1].second;        // == ci
+      Act up{h->CAT[l - 1], 2 * cn, cn, h->lH[l - 1], h->lW[l - 1]};
+      DAWN_TRY(upsample(c, h->up_conv[K], b, up, pre + ".4"));
+    } else {
+      Act xf{h->XR, 2 * dim, dim, H0, W0};
+      DAWN_TRY(temporal_attn(c, h->up_ta[K], b, xf, pre + ".3"));
+    }
+  }
+  Act xr{h->XR, 2 * dim, 2 * dim, H0, W0};
+  Act hf{h->HF, dim, dim, H0, W0}, ho{h->HO, dim, dim, H0, W0};
+  DAWN_TRY(resblock(c, h->rb[h->rb_index["final_conv.0"]], xr, hf));
+  DAWN_TRY(resblock(c, h->rb[h->rb_index["occlusion_map.0"]], xr, ho));
+  h->launches++;
+  DAWN_TRY(launch_heads_out(h->HF, h->HO, dim, F * H0 * W0, h->headW[0], h->headB[0], h->cfg.out_grid_dim,
+                            h->headW[1], h->headB[1], h->cfg.out_conf_dim, out, st));
+  return 0;
+}
+
+}  // namespace
+
+// ============================================================================================== C-ABI
+extern "C" {
+
+const char* dawn_last_error(void) { return g_last_error.c_str(); }
+const char* dawn_build_info(void) { return "dawn_unet sm_100a; contraction path: mma.sync 3xTF32 (+tcgen05 bf16x3 where enabled)"; }
+
+int dawn_unet_create(const dawn_unet_cfg* cfg, dawn_unet** out) {
+  DAWN_CHECK(cfg && out, "null argument");
+  DAWN_CHECK(cfg->attn_heads == 8 && cfg->attn_dim_head == 32, "only attn_heads=8, attn_dim_head=32 are supported");
+  DAWN_CHECK(cfg->resnet_groups == 8, "only resnet_groups=8 is supported");
+  DAWN_CHECK(cfg->dim % 64 == 0 && cfg->dim <= 128, "dim must be 64 or 128");
+  DAWN_CHECK(cfg->n_levels >= 2 && cfg->n_levels <= 6, "n_levels out of range");
+  DAWN_CHECK(cfg->init_kernel_size == 7 || cfg->init_kernel_size == 5 || cfg->init_kernel_size == 3, "init kernel must be 3, 5 or 7");
+  DAWN_CHECK(cfg->win_width >= 1 && cfg->win_width <= 120, "win_width out of range");
+  dawn_unet* h = new dawn_unet();
+  h->cfg = *cfg;
+  h->nlev = cfg->n_levels;
+  h->dims.push_back(cfg->dim);
+  for (int i = 0; i < cfg->n_levels; ++i) h->dims.push_back(cfg->dim * cfg->dim_mults[i]);
+  for (int i = 0; i < cfg->n_levels; ++i) h->in_out.push_back({h->dims[i], h->dims[i + 1]});
+  for (auto& io : h->in_out)
+    if (io.second > 1024 || io.second * 2 > 1024 + 1024) { delete h; set_last_error("channel count too large"); return -1; }
+  h->cond_dim = cfg->cond_aud + cfg->cond_pose + cfg->cond_eye;
+  h->tdim = 4 * cfg->dim;
+  h->cin_pad = round_up(cfg->channels, 32);
+  *out = h;
+  return 0;
+}
+
+void dawn_unet_destroy(dawn_unet* h) {
+  if (!h) return;
+  free_all(h->owned);
+  free_all(h->ws_owned);
+  delete h;
+}
+
+int dawn_unet_set_param(dawn_unet* h, const char* name, const float* host, const int64_t* shape, int ndim) {
+  DAWN_CHECK(h && name && host && (shape || ndim == 0), "null argument");
+  HostParam p;
+  p.shape.assign(shape, shape + ndim);
+  p.data.assign(host, host + p.numel());
+  h->raw[name] = std::move(p);
+  h->committed = false;
+  return 0;
+}
+
+int dawn_unet_commit_params(dawn_unet* h) {
+  DAWN_CHECK(h, "null handle");
+  free_all(h->owned);
+  h->rb.clear(); h->rb_index.clear();
+  h->down_ta.clear(); h->up_ta.clear(); h->down_sla.clear(); h->up_sla.clear(); h->down_conv.clear(); h->up_conv.clear();
+  const auto& cfg = h->cfg;
+  const int dim = cfg.dim, nlev = h->nlev, k = cfg.init_kernel_size;
+  // init conv: full (all input channels, padded) and the 3-channel slice for the hoisted path
+  DAWN_TRY(pack_conv(h, "init_conv", dim, cfg.channels, k, k, h->cin_pad, true, &h->init_full));
+  {
+    const HostParam* w;
+    DAWN_TRY(need(h, "init_conv.weight", {dim, cfg.channels, 1, k, k}, &w));
+    std::vector<float> w3((size_t)k * k * 3 * dim);
+    for (int t = 0; t < k * k; ++t)
+      for (int c = 0; c < 3; ++c)
+        for (int n = 0; n < dim; ++n) w3[((size_t)t * 3 + c) * dim + n] = w->data[((size_t)n * cfg.channels + c) * k * k + t];
+    DAWN_TRY(dev_upload(h, w3, &h->init_w3));
+  }
+  DAWN_TRY(upload_raw(h, "aux.time_freqs", {dim / 2}, &h->time_freqs));
+  DAWN_TRY(upload_raw(h, "aux.rel_bias", {8, 2 * cfg.win_width + 1}, &h->rel_bias));
+  DAWN_TRY(upload_raw(h, "time_mlp.1.weight", {h->tdim, dim}, &h->tW1));
+  DAWN_TRY(upload_raw(h, "time_mlp.1.bias", {h->tdim}, &h->tb1));
+  DAWN_TRY(upload_raw(h, "time_mlp.3.weight", {h->tdim, h->tdim}, &h->tW2));
+  DAWN_TRY(upload_raw(h, "time_mlp.3.bias", {h->tdim}, &h->tb2));
+  DAWN_TRY(upload_raw(h, "init_temporal_attn.fn.fn.fn.rotary_emb.freqs", {16}, &h->rot_freqs));
+  DAWN_TRY(pack_attn(h, "init_temporal_attn.fn.norm", "init_temporal_attn.fn.fn.fn", dim, &h->init_ta));
+  int stat_counter = 0;
+  for (int L = 0; L < nlev; ++L) {
+    const int ci = h->in_out[L].first, co = h->in_out[L].second;
+    const std::string pre = "downs." + std::to_string(L);
+    DAWN_TRY(pack_resblock(h, pre + ".0", ci, co, true, &stat_counter));
+    DAWN_TRY(pack_resblock(h, pre + ".1", co, co, true, &stat_counter));
+    SlaW s; DAWN_TRY(pack_sla(h, pre + ".2.fn", co, &s)); h->down_sla.push_back(s);
+    AttnW a; DAWN_TRY(pack_attn(h, pre + ".3.fn.norm", pre + ".3.fn.fn.fn", co, &a)); h->down_ta.push_back(a);
+    if (L < nlev - 1) {
+      ConvW d; DAWN_TRY(pack_conv(h, pre + ".4", co, co, 4, 4, co, true, &d)); h->down_conv.push_back(d);
+    }
+  }
+  const int mid = h->dims.back();
+  DAWN_TRY(pack_resblock(h, "mid_block1", mid, mid, true, &stat_counter));
+  DAWN_TRY(pack_attn(h, "mid_spatial_attn.fn.norm", "mid_spatial_attn.fn.fn.fn", mid, &h->mid_sa));
+  DAWN_TRY(pack_attn(h, "mid_temporal_attn.fn.norm", "mid_temporal_attn.fn.fn.fn", mid, &h->mid_ta));
+  DAWN_TRY(pack_resblock(h, "mid_block2", mid, mid, true, &stat_counter));
+  for (int K = 0; K < nlev; ++K) {
+    const int l = nlev - 1 - K;
+    const int ci = h->in_out[l].first, co = h->in_out[l].second;
+    const std::string pre = "ups." + std::to_string(K);
+    DAWN_TRY(pack_resblock(h, pre + ".0", 2 * co, ci, true, &stat_counter));
+    DAWN_TRY(pack_resblock(h, pre + ".1", ci, ci, true, &stat_counter));
+    SlaW s; DAWN_TRY(pack_sla(h, pre + ".2.fn", ci, &s)); h->up_sla.push_back(s);
+    AttnW a; DAWN_TRY(pack_attn(h, pre + ".3.fn.norm", pre + ".3.fn.fn.fn", ci, &a)); h->up_ta.push_back(a);
+    if (K < nlev - 1) {
+      UpW u; DAWN_TRY(pack_up(h, pre + ".4", ci, &u)); h->up_conv.push_back(u);
+    }
+  }
+  // heads: ResnetBlock_ca_mul without time/cond MLPs (their cross-attention parameters exist but never run, U:862, 875)
+  DAWN_TRY(pack_resblock(h, "final_conv.0", 2 * dim, dim, false, &stat_counter));
+  DAWN_TRY(pack_resblock(h, "occlusion_map.0", 2 * dim, dim, false, &stat_counter));
+  DAWN_TRY(upload_raw(h, "final_conv.1.weight", {cfg.out_grid_dim, dim, 1, 1, 1}, &h->headW[0]));
+  DAWN_TRY(upload_raw(h, "final_conv.1.bias", {cfg.out_grid_dim}, &h->headB[0]));
+  DAWN_TRY(upload_raw(h, "occlusion_map.1.weight", {cfg.out_conf_dim, dim, 1, 1, 1}, &h->headW[1]));
+  DAWN_TRY(upload_raw(h, "occlusion_map.1.bias", {cfg.out_conf_dim}, &h->headB[1]));
+  h->n_stats = stat_counter;
+  h->committed = true;
+  // a changed parameter set invalidates per-clip tables
+  h->have_invariants = false;
+  if (h->F > 0) return dawn_unet_set_num_frames(h, h->F, h->H, h->W);
+  return 0;
+}
+
+int dawn_unet_set_num_frames(dawn_unet* h, int F, int height, int width) {
+  DAWN_CHECK(h, "null handle");
+  DAWN_CHECK(h->committed, "commit_params must precede set_num_frames");
+  DAWN_CHECK(F >= 1 && F <= 65535, "F out of range");
+  const int nlev = h->nlev, dim = h->cfg.dim;
+  const int div = 1 << (nlev - 1);
+  DAWN_CHECK(height % div == 0 && width % div == 0 && height >= div && width >= div,
+             "latent height/width must be divisible by 2^(levels-1)");
+  free_all(h->ws_owned);
+  h->ws_bytes = 0;
+  h->have_invariants = false;
+  h->F = F; h->H = height; h->W = width;
+  h->lH.assign(nlev, 0); h->lW.assign(nlev, 0);
+  for (int l = 0; l < nlev; ++l) { h->lH[l] = height >> l; h->lW[l] = width >> l; }
+  auto& own = h->ws_owned;
+  const size_t P0 = (size_t)height * width, M0 = (size_t)F * P0;
+  int64_t* cnt = &h->ws_bytes;
+  DAWN_TRY(dev_alloc(own, M0 * h->cin_pad, &h->X288, cnt));
+  DAWN_TRY(dev_alloc(own, P0 * h->cin_pad, &h->FEA288, cnt));
+  DAWN_TRY(dev_alloc(own, P0 * dim, &h->MAP, cnt));
+  DAWN_TRY(dev_alloc(own, M0 * 2 * dim, &h->XR, cnt));
+  DAWN_TRY(dev_alloc(own, M0 * dim, &h->S0, cnt));
+  h->bufA.assign(nlev, nullptr); h->bufB.assign(nlev, nullptr); h->CAT.assign(nlev, nullptr); h->DS.assign(nlev, nullptr);
+  size_t max_mc = 0, max_bf = 0;
+  for (int l = 0; l < nlev; ++l) {
+    const size_t Ml = (size_t)F * h->lH[l] * h->lW[l];
+    const int ci = h->in_out[l].first, co = h->in_out[l].second;
+    DAWN_TRY(dev_alloc(own, Ml * co, &h->bufA[l], cnt));
+    DAWN_TRY(dev_alloc(own, Ml * co, &h->bufB[l], cnt));
+    DAWN_TRY(dev_alloc(own, Ml * 2 * co, &h->CAT[l], cnt));
+    if (l > 0) DAWN_TRY(dev_alloc(own, Ml * ci, &h->DS[l], cnt));
+    max_mc = std::max(max_mc, Ml * co);
+    max_bf = std::max(max_bf, (size_t)F * 256 * round_up(co, 64));
+  }
+  max_mc = std::max(max_mc, M0 * dim);
+  DAWN_TRY(dev_alloc(own, max_mc, &h->Y, cnt));
+  DAWN_TRY(dev_alloc(own, max_mc, &h->A1, cnt));
+  DAWN_TRY(dev_alloc(own, M0 * 768, &h->QKV, cnt));
+  DAWN_TRY(dev_alloc(own, M0 * 256, &h->O, cnt));
+  DAWN_TRY(dev_alloc(own, M0 * 2, &h->ROWSTATS, cnt));
+  DAWN_TRY(dev_alloc(own, M0 * 24, &h->GATES, cnt));
+  DAWN_TRY(dev_alloc(own, M0 * 32, &h->WT, cnt));
+  DAWN_TRY(dev_alloc(own, max_bf, &h->BF, cnt));
+  DAWN_TRY(dev_alloc(own, M0 * dim, &h->HF, cnt));
+  DAWN_TRY(dev_alloc(own, M0 * dim, &h->HO, cnt));
+  DAWN_TRY(dev_alloc(own, (size_t)F * 32, &h->ROT, cnt));
+  DAWN_TRY(dev_alloc(own, h->tdim, &h->TSILU, cnt));
+  DAWN_TRY(dev_alloc(own, (size_t)F * 2048, &h->CTX, cnt));
+  DAWN_TRY(dev_alloc(own, (size_t)F * 128, &h->KV, cnt));
+  {
+    float* s; DAWN_TRY(dev_alloc(own, (size_t)h->n_stats * 32, &s, cnt)); h->STATS = (double*)s;
+    float* t; DAWN_TRY(dev_alloc(own, 4, &t, cnt)); h->T_HOSTSIDE = (int64_t*)t;
+  }
+  DAWN_TRY(dev_alloc(own, 3 * M0, &h->H_XT, cnt));
+  DAWN_TRY(dev_alloc(own, (size_t)(h->cfg.channels - 3) * P0, &h->H_FEA, cnt));
+  DAWN_TRY(dev_alloc(own, (size_t)F * h->cond_dim, &h->H_COND, cnt));
+  DAWN_TRY(dev_alloc(own, (size_t)(h->cfg.out_grid_dim + h->cfg.out_conf_dim) * M0, &h->H_OUT, cnt));
+  // per-block per-clip tables
+  std::vector<FilmDesc> descs;
+  for (auto& r : h->rb) {
+    if (!r.cond) continue;
+    r.ldbT = round_up(r.co, 64);
+    DAWN_TRY(dev_alloc(own, 2 * r.co, &r.film, cnt));
+    DAWN_TRY(dev_alloc(own, (size_t)F * 3 * 64, &r.kq, cnt));
+    DAWN_TRY(dev_alloc(own, 24, &r.nkq, cnt));
+    DAWN_TRY(dev_alloc(own, (size_t)F * 32 * r.ldbT, &r.T, cnt));
+    DAWN_CUDA_OK(cudaMemset(r.T, 0, (size_t)F * 32 * r.ldbT * sizeof(float)));
+    DAWN_TRY(dev_alloc(own, (size_t)F * 3 * 81, &r.G, cnt));
+    descs.push_back(FilmDesc{r.tW, r.tB, r.film, 2 * r.co});
+  }
+  {
+    float* d; DAWN_TRY(dev_alloc(own, descs.size() * sizeof(FilmDesc) / sizeof(float) + 4, &d, cnt));
+    DAWN_CUDA_OK(cudaMemcpy(d, descs.data(), descs.size() * sizeof(FilmDesc), cudaMemcpyHostToDevice));
+    h->film_descs = (FilmDesc*)d; h->n_film = (int)descs.size();
+  }
+  DAWN_TRY(launch_rotary_table(h->rot_freqs, F, 0, h->ROT, 0));
+  DAWN_CUDA_OK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int dawn_unet_set_clip_invariants(dawn_unet* h, const float* fea, const float* cond, void* stream) {
+  DAWN_CHECK(h && fea && cond, "null argument");
+  DAWN_CHECK(h->F > 0, "set_num_frames must precede set_clip_invariants");
+  cudaStream_t st = (cudaStream_t)stream;
+  Ctx c{h, st};
+  const int H0 = h->lH[0], W0 = h->lW[0], dim = h->cfg.dim, k = h->cfg.init_kernel_size;
+  // per-clip constant part of the init conv: conv(cat[0, fea]) + bias  (linearity)
+  h->launches++;
+  DAWN_TRY(launch_ncf_to_nhwc(fea, h->cfg.channels - 3, 1, H0 * W0, h->cin_pad, 3, h->FEA288, st));
+  {
+    Act in{h->FEA288, h->cin_pad, h->cin_pad, H0, W0};
+    GemmParams p; base_params(p, in, 1);
+    set_weights(p, h->init_full); set_square_taps(p, k, k / 2);
+    p.Out = h->MAP; p.ldo = dim;
+    DAWN_TRY(c.gemm(p, EPI_PLAIN));
+  }
+  DAWN_TRY(prep_cond(h, cond, st));
+  h->have_invariants = true;
+  return 0;
+}
+
+int dawn_unet_forward(dawn_unet* h, const float* x, const int64_t* t, const float* cond, float* out, void* stream) {
+  DAWN_CHECK(h && x && t && cond && out, "null argument");
+  DAWN_CHECK(h->F > 0, "set_num_frames must precede forward");
+  cudaStream_t st = (cudaStream_t)stream;
+  h->launches = 0;
+  Ctx c{h, st};
+  const int H0 = h->lH[0], W0 = h->lW[0], dim = h->cfg.dim, k = h->cfg.init_kernel_size;
+  DAWN_TRY(prep_cond(h, cond, st));
+  h->have_invariants = false;         // MAP not refreshed by this entry
+  h->launches++;
+  DAWN_TRY(launch_ncf_to_nhwc(x, h->cfg.channels, h->F, H0 * W0, h->cin_pad, 0, h->X288, st));
+  {
+    Act in{h->X288, h->cin_pad, h->cin_pad, H0, W0};
+    GemmParams p; base_params(p, in, h->F);
+    set_weights(p, h->init_full); set_square_taps(p, k, k / 2);
+    p.Out = h->XR + dim; p.ldo = 2 * dim;
+    DAWN_TRY(c.gemm(p, EPI_PLAIN));
+  }
+  return forward_core(h, t, out, st);
+}
+
+int dawn_unet_forward_x3(dawn_unet* h, const float* x_t, const int64_t* t, float* out, void* stream) {
+  DAWN_CHECK(h && x_t && t && out, "null argument");
+  DAWN_CHECK(h->F > 0 && h->have_invariants, "set_clip_invariants must precede forward_x3");
+  cudaStream_t st = (cudaStream_t)stream;
+  h->launches = 0;
+  const int H0 = h->lH[0], W0 = h->lW[0], dim = h->cfg.dim;
+  h->launches++;
+  DAWN_TRY(launch_init_conv_x3(x_t, h->F, H0, W0, h->init_w3, h->MAP, dim, h->XR + dim, 2 * dim,
+                               h->cfg.init_kernel_size, st));
+  return forward_core(h, t, out, st);
+}
+
+int dawn_unet_forward_host(dawn_unet* h, const float* x_t, const float* fea, const float* cond, int64_t t, float* out) {
+  DAWN_CHECK(h && x_t && fea && cond && out, "null argument");
+  DAWN_CHECK(h->F > 0, "set_num_frames must precede forward_host");
+  cudaStream_t st = 0;
+  const size_t M0 = (size_t)h->F * h->H * h->W, P0 = (size_t)h->H * h->W;
+  const size_t nout = (size_t)(h->cfg.out_grid_dim + h->cfg.out_conf_dim) * M0;
+  DAWN_CUDA_OK(cudaMemcpyAsync(h->H_XT, x_t, 3 * M0 * sizeof(float), cudaMemcpyHostToDevice, st));
+  DAWN_CUDA_OK(cudaMemcpyAsync(h->H_FEA, fea, (size_t)(h->cfg.channels - 3) * P0 * sizeof(float), cudaMemcpyHostToDevice, st));
+  DAWN_CUDA_OK(cudaMemcpyAsync(h->H_COND, cond, (size_t)h->F * h->cond_dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  DAWN_CUDA_OK(cudaMemcpyAsync(h->T_HOSTSIDE, &t, sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  DAWN_TRY(dawn_unet_set_clip_invariants(h, h->H_FEA, h->H_COND, st));
+  const int64_t prep_launches = h->launches;
+  DAWN_TRY(dawn_unet_forward_x3(h, h->H_XT, h->T_HOSTSIDE, h->H_OUT, st));
+  h->launches += prep_launches;
+  DAWN_CUDA_OK(cudaMemcpyAsync(out, h->H_OUT, nout * sizeof(float), cudaMemcpyDeviceToHost, st));
+  DAWN_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int dawn_unet_tap_shape(dawn_unet* h, const char* name, int* C, int* hl, int* wl) {
+  DAWN_CHECK(h && name && C && hl && wl && h->F > 0, "bad argument");
+  const std::string n(name);
+  const int nlev = h->nlev, dim = h->cfg.dim;
+  auto set = [&](int c, int l) { *C = c; *hl = h->lH[l]; *wl = h->lW[l]; return 0; };
+  if (n == "init_conv" || n == "init_temporal_attn" || n == "final_conv.0" || n == "occlusion_map.0") return set(dim, 0);
+  if (n.rfind("mid_", 0) == 0) return set(h->dims.back(), nlev - 1);
+  int L = -1, j = -1;
+  if (sscanf(name, "downs.%d.%d", &L, &j) == 2 && L >= 0 && L < nlev) {
+    if (j == 4) { DAWN_CHECK(L < nlev - 1, "no such tap"); return set(h->in_out[L].second, L + 1); }
+    return set(h->in_out[L].second, L);
+  }
+  if (sscanf(name, "ups.%d.%d", &L, &j) == 2 && L >= 0 && L < nlev) {
+    const int l = nlev - 1 - L;
+    if (j == 4) { DAWN_CHECK(L < nlev - 1, "no such tap"); return set(h->in_out[l].first, l - 1); }
+    return set(h->in_out[l].first, l);
+  }
+  set_last_error("unknown tap: " + n);
+  return -1;
+}
+
+int dawn_unet_set_tap(dawn_unet* h, const char* name, float* dst) {
+  DAWN_CHECK(h && name, "null argument");
+  if (dst) h->taps[name] = dst; else h->taps.erase(name);
+  return 0;
+}
+
+int64_t dawn_unet_last_launch_count(dawn_unet* h) { return h ? h->launches : 0; }
+int64_t dawn_unet_workspace_bytes(dawn_unet* h) { return h ? h->ws_bytes : 0; }
+
+}  // extern "C"

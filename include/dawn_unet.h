@@ -1,0 +1,95 @@
+/* dawn_unet.h — C-ABI of the B200-native DAWN denoising UNet (one "denoising step").
+ *
+ * The reference has no FFI layer: its seam is the Python nn.Module `DynamicNfUnet3D`
+ * (DM_3/modules/video_flow_diffusion_multiGPU_v0_crema_plus_faceemb_ca_multi_test.py:728-965) held by
+ * `GaussianDiffusion.denoise_fn` (same file :1010) and `FlowDiffusion.unet`
+ * (..._flow_fast_init_cond_test.py:140).  The entry points below are what a binding for that seam needs;
+ * dawn_pytorch_b200/unet.py is the ctypes binding that keeps the reference's Python signature on top of them.
+ * Plain pointers and sizes only; no torch types.  One handle per GPU, not thread-safe, stream-ordered,
+ * no hidden host synchronisation inside forward calls.  All tensors are fp32; one clip (batch element) per call.
+ *
+ * Return value: 0 ok; -1 bad argument / unsupported configuration / wrong call order; -2 CUDA error.
+ * dawn_last_error() returns a human-readable description of the last failure on this thread.
+ */
+#ifndef DAWN_UNET_H_
+#define DAWN_UNET_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dawn_unet dawn_unet;
+
+/* Constructor arguments of Unet3D.__init__ (reference :729-753) that change the network's shape. */
+typedef struct {
+  int dim;              /* 64 */
+  int n_levels;         /* len(dim_mults) = 4 */
+  int dim_mults[8];     /* (1,2,4,8) */
+  int channels;         /* 275 = 3 + 256 + 16 */
+  int cond_aud;         /* 1024 */
+  int cond_pose;        /* 6 */
+  int cond_eye;         /* 2 */
+  int out_grid_dim;     /* 2 */
+  int out_conf_dim;     /* 1 */
+  int attn_heads;       /* 8  (only 8 supported) */
+  int attn_dim_head;    /* 32 (only 32 supported) */
+  int resnet_groups;    /* 8  (only 8 supported) */
+  int init_kernel_size; /* 7 */
+  int win_width;        /* 40: temporal attention attends |i-j| <= win_width (reference :117) */
+} dawn_unet_cfg;
+
+/* replaces Unet3D.__init__ / DynamicNfUnet3D.__init__ (reference :728-877, 959-963) */
+int dawn_unet_create(const dawn_unet_cfg* cfg, dawn_unet** out);
+void dawn_unet_destroy(dawn_unet* h);
+
+/* replaces nn.Module.load_state_dict (unified_video_generator.py:527-528): `name` is the reference
+ * state_dict key, `host` a host pointer to the fp32 values, row-major in `shape`.
+ * Two auxiliary host-computed tables use the same call:
+ *   "aux.time_freqs"  (dim/2,)      SinusoidalPosEmb frequencies (reference :157-159)
+ *   "aux.rel_bias"    (heads, 2w+1) RelativePositionBias values for rel = -w..w (reference :111-119)  */
+int dawn_unet_set_param(dawn_unet* h, const char* name, const float* host, const int64_t* shape, int ndim);
+/* repack all parameters into kernel layouts and upload; must follow the last set_param */
+int dawn_unet_commit_params(dawn_unet* h);
+
+/* replaces DynamicNfUnet3D.update_num_frames (reference :964-965) and fixes the latent size.
+ * frame_lo/frame_hi select the frames this GPU owns when a clip is sharded by frame window across ranks
+ * (0, F for a whole clip); halo frames for temporal attention are exchanged by the caller. */
+int dawn_unet_set_num_frames(dawn_unet* h, int F, int height, int width);
+
+/* Clip invariants: the 272 feature channels are identical for every frame and every
+ * DDIM step (reference :1167 `fea.repeat`), and cross-attention keys/values depend only on `cond`.
+ * fea: device (channels-3, height, width); cond: device (F, cond_dim).  Needed by dawn_unet_forward_x3. */
+int dawn_unet_set_clip_invariants(dawn_unet* h, const float* fea, const float* cond, void* stream);
+
+/* replaces Unet3D.forward / forward_with_cond_scale(cond_scale=1) (reference :879-956) for one clip:
+ * x: device (channels, F, height, width); t: device int64[1]; cond: device (F, cond_dim);
+ * out: device (out_grid_dim + out_conf_dim, F, height, width). */
+int dawn_unet_forward(dawn_unet* h, const float* x, const int64_t* t, const float* cond, float* out, void* stream);
+
+/* same function when the caller knows the clip invariants: x_t: device (3, F, height, width) */
+int dawn_unet_forward_x3(dawn_unet* h, const float* x_t, const int64_t* t, float* out, void* stream);
+
+/* end-to-end entry with HOST buffers (pinned recommended): copies x_t, fea, cond, t to the device,
+ * runs set_clip_invariants + forward_x3 and copies the result back; returns after the stream is synchronised. */
+int dawn_unet_forward_host(dawn_unet* h, const float* x_t, const float* fea, const float* cond, int64_t t, float* out);
+
+/* debugging / sub-module parity: request a copy of an internal activation (names as in oracle/unet_oracle.py
+ * taps, e.g. "downs.1.0") into dst (device, (C, F, h_l, w_l)) during the next forward calls; dst = NULL clears. */
+int dawn_unet_set_tap(dawn_unet* h, const char* name, float* dst);
+/* channels and spatial size of a tap for the current set_num_frames: writes C, h_l, w_l */
+int dawn_unet_tap_shape(dawn_unet* h, const char* name, int* C, int* hl, int* wl);
+
+/* number of kernels launched by the last forward on this handle (bench.py's gpu_launches) */
+int64_t dawn_unet_last_launch_count(dawn_unet* h);
+/* bytes of device workspace currently held */
+int64_t dawn_unet_workspace_bytes(dawn_unet* h);
+
+const char* dawn_last_error(void);
+const char* dawn_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAWN_UNET_H_ */

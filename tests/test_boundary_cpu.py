@@ -1,0 +1,90 @@
+"""CPU: the drop-in boundary — module mirror of the reference state_dict, C-ABI symbols, host-side logic."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CTOR = dict(dim=64, cond_dim=1032, cond_aud=1024, cond_pose=6, cond_eye=2, num_frames=40, channels=275,
+            out_grid_dim=2, out_conf_dim=1, dim_mults=(1, 2, 4, 8), use_hubert_audio_cond=True,
+            learn_null_cond=False, use_final_activation=False, use_deconv=True, padding_mode="zeros", win_width=40)
+
+
+def test_library_exports_every_declared_symbol():
+    from dawn_pytorch_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "dawn_unet.h")).read()
+    declared = set(re.findall(r"\b(dawn_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for sym in declared:
+        assert hasattr(_lib.lib, sym), f"{sym} declared in include/dawn_unet.h but not exported"
+    assert declared == set(_lib.EXPORTS)
+    assert b"sm_100a" in _lib.lib.dawn_build_info()
+
+
+def test_state_dict_schema_equals_reference(schema):
+    from dawn_pytorch_b200 import DynamicNfUnet3D
+    net = DynamicNfUnet3D(**CTOR)
+    mine = [(k, list(v.shape)) for k, v in net.state_dict().items()]
+    ref = [(k, list(s)) for k, s in schema["entries"]]
+    assert len(mine) == len(ref) == 900
+    assert dict(mine) == dict(ref)
+    assert [k for k, _ in mine] == [k for k, _ in ref], "same registration order as the reference"
+    assert net.num_frames == 20 and net.has_cond
+
+
+def test_load_reference_style_state_dict_and_api_surface(synth_sd):
+    from dawn_pytorch_b200 import DynamicNfUnet3D
+    net = DynamicNfUnet3D(**CTOR).eval()
+    missing = net.load_state_dict(synth_sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    net.update_num_frames(16)
+    assert net.num_frames == 16
+    for attr in ("forward", "forward_with_cond_scale", "update_num_frames", "null_cond_mask", "has_cond"):
+        assert hasattr(net, attr)
+
+
+def test_cpu_tensors_fail_loudly(synth_sd):
+    """No CPU fallback: calling the module with CPU tensors must raise, not silently compute."""
+    from dawn_pytorch_b200 import DynamicNfUnet3D
+    from dawn_pytorch_b200._lib import DawnError
+    net = DynamicNfUnet3D(**CTOR).eval()
+    net.update_num_frames(4)
+    with pytest.raises(DawnError):
+        net.forward_with_cond_scale(torch.zeros(1, 275, 4, 8, 8), torch.zeros(1, dtype=torch.long),
+                                    cond=torch.zeros(1, 4, 1032), cond_scale=1.0)
+
+
+def test_c_abi_argument_checks_without_gpu():
+    from dawn_pytorch_b200 import _lib
+    lib = _lib.lib
+    cfg = _lib.DawnUnetCfg()
+    cfg.dim, cfg.n_levels = 64, 4
+    for i, m in enumerate((1, 2, 4, 8)):
+        cfg.dim_mults[i] = m
+    cfg.channels, cfg.cond_aud, cfg.cond_pose, cfg.cond_eye = 275, 1024, 6, 2
+    cfg.out_grid_dim, cfg.out_conf_dim, cfg.attn_heads, cfg.attn_dim_head, cfg.resnet_groups = 2, 1, 8, 32, 8
+    cfg.init_kernel_size, cfg.win_width = 7, 40
+    h = ctypes.c_void_p()
+    assert lib.dawn_unet_create(ctypes.byref(cfg), ctypes.byref(h)) == 0
+    # wrong call order is an error, not a crash
+    assert lib.dawn_unet_set_num_frames(h, 16, 32, 32) == -1
+    assert b"commit_params" in lib.dawn_last_error()
+    lib.dawn_unet_destroy(h)
+    cfg.attn_heads = 4
+    assert lib.dawn_unet_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    assert b"attn_heads" in lib.dawn_last_error()
+
+
+def test_rel_bias_table_matches_oracle(synth_sd):
+    from dawn_pytorch_b200.unet import _rel_bias_table, _time_freqs
+    from oracle import unet_oracle as O
+    w = synth_sd["time_rel_pos_bias.relative_attention_bias.weight"]
+    full = O.rel_pos_bias(w, 200, 40)                      # (8, 200, 200) incl. -1e8 mask
+    tab = _rel_bias_table(w, 40)                           # (8, 81)
+    for i in (0, 57, 199):
+        for j in range(max(0, i - 40), min(200, i + 41)):
+            assert torch.equal(full[:, i, j], tab[:, j - i + 40])
+    assert torch.equal(O.sinusoidal(torch.tensor([500]), 64)[0, :32], torch.sin(500 * _time_freqs(64)))
