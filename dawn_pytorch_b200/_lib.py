@@ -22,7 +22,7 @@ class DawnError(RuntimeError):
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m dawn_pytorch_b200.build` "
+            f"{LIB_PATH} is missing: build it with `python dawn_pytorch_b200/build.py` "
             "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the DAWN denoising UNet.")
     lib = ctypes.CDLL(LIB_PATH)
     vp, i64p, fp, cp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p, ctypes.c_char_p
@@ -39,6 +39,9 @@ def _load():
     lib.dawn_unet_set_tap.argtypes = [vp, cp, fp]
     lib.dawn_unet_tap_shape.argtypes = [vp, cp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
                                         ctypes.POINTER(ctypes.c_int)]
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.dawn_unet_profile_enable.argtypes = [vp, ctypes.c_int]
+    lib.dawn_unet_profile_read.argtypes = [vp, dp, dp, dp, i64p]
     lib.dawn_unet_last_launch_count.argtypes = [vp]
     lib.dawn_unet_last_launch_count.restype = ctypes.c_int64
     lib.dawn_unet_workspace_bytes.argtypes = [vp]
@@ -53,7 +56,12 @@ lib = _load()
 EXPORTS = ["dawn_unet_create", "dawn_unet_destroy", "dawn_unet_set_param", "dawn_unet_commit_params",
            "dawn_unet_set_num_frames", "dawn_unet_set_clip_invariants", "dawn_unet_forward",
            "dawn_unet_forward_x3", "dawn_unet_forward_host", "dawn_unet_set_tap", "dawn_unet_tap_shape",
-           "dawn_unet_last_launch_count", "dawn_unet_workspace_bytes", "dawn_last_error", "dawn_build_info"]
+           "dawn_unet_profile_enable", "dawn_unet_profile_read", "dawn_unet_last_launch_count", "dawn_unet_workspace_bytes", "dawn_last_error", "dawn_build_info"]
+
+
+PROF_CATS = ["conv3x3", "conv_other", "qkv_proj", "out_proj", "ca_gate", "gn_hcond", "attn_core", "sla_context",
+             "gn_apply", "rowstats", "ca_rstd", "misc", "prep"]
+PROF_NCAT = 16
 
 
 def check(rc, what):

@@ -1,4 +1,4 @@
-"""Build libdawn_unet.so (sm_100a only) in-tree with nvcc.  `python -m dawn_pytorch_b200.build [--force]`."""
+"""Build libdawn_unet.so (sm_100a only) in-tree with nvcc.  `python dawn_pytorch_b200/build.py [--force]`."""
 import hashlib
 import os
 import subprocess

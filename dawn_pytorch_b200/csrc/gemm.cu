@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_kernel(const GemmParams p) {
     const float* bs = Bs + (kc % STAGES) * BK * B_LD + wn * 32;
 #pragma unroll
     for (int ks = 0; ks < BK / 8; ++ks) {
-      uint32_t ahi[2][4], alo[2][4], bhi[4][2], blo[4][2];
+      uint32_t ahi[2][4], alo[2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         const float* a = as + (mt * 16 + g) * A_LD + ks * 8 + t4;
@@ -126,20 +126,25 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_kernel(const GemmParams p) {
         split_tf32(a[4], ahi[mt][2], alo[mt][2]);
         split_tf32(a[8 * A_LD + 4], ahi[mt][3], alo[mt][3]);
       }
+      // The tensor core accumulates with round-toward-zero; chained over K that bias grows ~K*2^-24
+      // (measured on B200: 1.4e-4 at K=14112).  So each k-step's 3-term product lands in a zeroed
+      // fragment and is added to the running sum with an ordinary round-to-nearest FADD.
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
+        uint32_t bhi[2], blo[2];
         const float* b = bs + (ks * 8 + t4) * B_LD + nt * 8 + g;
-        split_tf32(b[0], bhi[nt][0], blo[nt][0]);
-        split_tf32(b[4 * B_LD], bhi[nt][1], blo[nt][1]);
-      }
+        split_tf32(b[0], bhi[0], blo[0]);
+        split_tf32(b[4 * B_LD], bhi[1], blo[1]);
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < 2; ++mt) {
+          float d[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_tf32(d, alo[mt], bhi);
+          mma_tf32(d, ahi[mt], blo);
+          mma_tf32(d, ahi[mt], bhi);
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          mma_tf32(acc[mt][nt], alo[mt], bhi[nt]);
-          mma_tf32(acc[mt][nt], ahi[mt], blo[nt]);
-          mma_tf32(acc[mt][nt], ahi[mt], bhi[nt]);
+          for (int i = 0; i < 4; ++i) acc[mt][nt][i] += d[i];
         }
+      }
     }
   }
   cp_async_wait<0>();

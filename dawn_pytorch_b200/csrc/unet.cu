@@ -116,6 +116,17 @@ struct dawn_unet {
 
   std::map<std::string, float*> taps;
   int64_t launches = 0;
+
+  // per-category kernel timing (CUDA events on the launching stream), see dawn_unet_profile_*
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  size_t prof_used = 0;
+  struct ProfRec { int cat; double flops; double bytes; };
+  std::vector<ProfRec> prof_recs;
+  double prof_ms[DAWN_PROF_NCAT] = {0};
+  double prof_flops[DAWN_PROF_NCAT] = {0};
+  double prof_bytes[DAWN_PROF_NCAT] = {0};
+  int64_t prof_cnt[DAWN_PROF_NCAT] = {0};
 };
 
 namespace {
@@ -347,10 +358,60 @@ void set_square_taps(GemmParams& p, int k, int pad) {
     for (int kx = 0; kx < k; ++kx) { p.dy[ky * k + kx] = (signed char)(ky - pad); p.dx[ky * k + kx] = (signed char)(kx - pad); }
 }
 
+
+// profile categories (dawn_unet_profile_read)
+enum ProfCat : int {
+  PC_CONV3 = 0,      // 3x3 conv implicit GEMM (+GroupNorm statistics)
+  PC_CONV_OTHER,     // init 7x7, 4x4 down / transposed up, 1x1 residual convs
+  PC_QKV,            // LayerNorm-folded qkv projections (temporal / spatial-linear / mid attention)
+  PC_OUTPROJ,        // attention output projections (+ residual)
+  PC_CA_GATE,        // cross-attention q projection + 2-key softmax gate
+  PC_GN_HCOND,       // SiLU(FiLM(GN)) + per-frame cross-attention table GEMM (K=32)
+  PC_ATTN_CORE,      // banded temporal / full spatial softmax attention
+  PC_SLA_CTX,        // spatial linear attention context + composed projection
+  PC_GN_APPLY,       // elementwise SiLU(GN) (+ residual)
+  PC_ROWSTATS,       // LayerNorm row statistics
+  PC_CA_RSTD,        // cross-attention output LayerNorm via Gram form
+  PC_MISC,           // time MLP, FiLM, init conv (3 ch), heads, layout
+  PC_PREP,           // per-clip tables
+  PC_COUNT
+};
+static_assert(PC_COUNT <= DAWN_PROF_NCAT, "increase DAWN_PROF_NCAT");
+
 struct Ctx {
   dawn_unet* h; cudaStream_t st;
-  int gemm(const GemmParams& p, int epi) { h->launches++; return launch_gemm(p, epi, st); }
+  int gemm(const GemmParams& p, int epi, int cat);
 };
+
+// one kernel launch: counted, and bracketed by CUDA events when profiling is on
+struct ProfScope {
+  dawn_unet* h; cudaStream_t st; bool on;
+  ProfScope(Ctx& c, int cat, double flops, double bytes) : h(c.h), st(c.st), on(c.h->prof_on) {
+    h->launches++;
+    if (!on) return;
+    while (h->prof_ev.size() < h->prof_used + 2) {
+      cudaEvent_t e; cudaEventCreate(&e); h->prof_ev.push_back(e);
+    }
+    h->prof_recs.push_back({cat, flops, bytes});
+    cudaEventRecord(h->prof_ev[h->prof_used], st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(h->prof_ev[h->prof_used + 1], st);
+    h->prof_used += 2;
+  }
+};
+
+int Ctx::gemm(const GemmParams& p, int epi, int cat) {
+  // algorithmic work: 2*M*N*K flops (1x, not the 3 split passes); bytes: A once + output write (+ residual/Y read)
+  const double flops = 2.0 * p.M * (double)p.N * p.K;
+  double bytes = 4.0 * p.M * ((double)p.Cin * (p.in_stride == 1 ? 1 : 4) + p.N);
+  if (p.Res) bytes += 4.0 * p.M * p.N;
+  if (p.Y) bytes += 4.0 * p.M * p.N;
+  if (epi == EPI_CA_GATE) bytes = 4.0 * p.M * (p.Cin + 24.0);
+  ProfScope ps(*this, cat, flops, bytes);
+  return launch_gemm(p, epi, st);
+}
 
 int tap(Ctx& c, const std::string& name, const Act& a);
 
@@ -360,7 +421,7 @@ int conv_same(Ctx& c, const Act& in, const ConvW& w, int k, const Act& out, int 
   set_weights(p, w); set_square_taps(p, k, k / 2);
   p.Out = out.p; p.ldo = out.ld;
   if (stat_slot >= 0) { p.stats = c.h->STATS + 16 * stat_slot; p.cpg = w.N / 8; }
-  return c.gemm(p, EPI_PLAIN);
+  return c.gemm(p, EPI_PLAIN, k == 3 ? PC_CONV3 : PC_CONV_OTHER);
 }
 
 // ResnetBlock_ca_mul (U:363-479)
@@ -372,13 +433,15 @@ int resblock(Ctx& c, const ResBlockW& r, const Act& x, const Act& out) {
   const double count = (double)M * (r.co / 8);
   if (r.cond) {
     // cross-attention gates from the raw block input (U:454-463): LayerNorm_img folded into the q projection
-    h->launches++;
-    DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
+    {
+      ProfScope ps(c, PC_ROWSTATS, 0, 4.0 * M * x.C);
+      DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
+    }
     GemmParams p; base_params(p, x, F);
     p.B = r.Wq; p.ldb = 192; p.N = 192; p.K = r.ci;
     p.rowstats = h->ROWSTATS; p.wsum = r.wsumq; p.kq = r.kq; p.nkq = r.nkq; p.gates = h->GATES;
-    DAWN_TRY(c.gemm(p, EPI_CA_GATE));
-    h->launches++;
+    DAWN_TRY(c.gemm(p, EPI_CA_GATE, PC_CA_GATE));
+    ProfScope ps(c, PC_CA_RSTD, 0, 4.0 * M * 56);
     DAWN_TRY(launch_ca_rstd(h->GATES, r.G, M, P, h->WT, c.st));
   }
   DAWN_TRY(conv_same(c, x, r.c1, 3, y, r.st1));
@@ -391,9 +454,9 @@ int resblock(Ctx& c, const ResBlockW& r, const Act& x, const Act& out) {
     p.Out = a1.p; p.ldo = a1.ld;
     p.Y = y.p; p.ldy = y.ld; p.gn_stats = h->STATS + 16 * r.st1; p.gn_w = r.gn1w; p.gn_b = r.gn1b;
     p.film = r.film; p.gn_count = count; p.cpg = r.co / 8;
-    DAWN_TRY(c.gemm(p, EPI_GN_APPLY));
+    DAWN_TRY(c.gemm(p, EPI_GN_APPLY, PC_GN_HCOND));
   } else {
-    h->launches++;
+    ProfScope ps(c, PC_GN_APPLY, 0, 8.0 * M * r.co);
     DAWN_TRY(launch_gn_apply(y.p, y.ld, r.co, M, h->STATS + 16 * r.st1, count, r.co / 8, r.gn1w, r.gn1b, nullptr,
                              nullptr, 0, a1.p, a1.ld, c.st));
   }
@@ -403,12 +466,14 @@ int resblock(Ctx& c, const ResBlockW& r, const Act& x, const Act& out) {
     GemmParams p; base_params(p, x, F);
     set_weights(p, r.cres);
     p.Out = out.p; p.ldo = out.ld;
-    DAWN_TRY(c.gemm(p, EPI_PLAIN));
+    DAWN_TRY(c.gemm(p, EPI_PLAIN, PC_CONV_OTHER));
     res = out.p; ldr = out.ld;
   }
-  h->launches++;
+  {
+  ProfScope ps(c, PC_GN_APPLY, 0, 12.0 * M * r.co);
   DAWN_TRY(launch_gn_apply(y.p, y.ld, r.co, M, h->STATS + 16 * r.st2, count, r.co / 8, r.gn2w, r.gn2b, nullptr,
                            res, ldr, out.p, out.ld, c.st));
+  }
   return tap(c, r.name, out);
 }
 
@@ -416,21 +481,25 @@ int resblock(Ctx& c, const ResBlockW& r, const Act& x, const Act& out) {
 int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const std::string& name) {
   dawn_unet* h = c.h;
   const int F = h->F, P = x.H * x.W, M = F * P;
-  h->launches++;
-  DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
+  {
+    ProfScope ps(c, PC_ROWSTATS, 0, 4.0 * M * x.C);
+    DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
+  }
   {
     GemmParams p; base_params(p, x, F);
     p.B = w.Wqkv; p.ldb = 768; p.N = 768; p.K = x.C;
     p.rowstats = h->ROWSTATS; p.wsum = w.wsum; p.rot = h->ROT;
     p.Out = h->QKV; p.ldo = 768;
-    DAWN_TRY(c.gemm(p, EPI_QKV_TEMPORAL));
+    DAWN_TRY(c.gemm(p, EPI_QKV_TEMPORAL, PC_QKV));
   }
   {
     AttnArgs a{};
     a.qkv = h->QKV; a.ld = 768; a.out = h->O; a.ldo = 256;
     a.nseq = P; a.L = F; a.seq_base_stride = 1; a.elem_stride = P;
     a.band = h->cfg.win_width; a.bias = h->rel_bias; a.q_lo = 0; a.q_hi = F;
-    h->launches++;
+    double pairs = 0;
+    for (int i = 0; i < F; ++i) pairs += std::min(F - 1, i + a.band) - std::max(0, i - a.band) + 1;
+    ProfScope ps(c, PC_ATTN_CORE, 4.0 * 32 * 8 * P * pairs, 4.0 * M * 1024);
     DAWN_TRY(launch_attention(a, c.st));
   }
   {
@@ -438,7 +507,7 @@ int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const st
     GemmParams p; base_params(p, o, F);
     set_weights(p, w.out);
     p.Res = x.p; p.ldr = x.ld; p.Out = dst.p; p.ldo = dst.ld;
-    DAWN_TRY(c.gemm(p, EPI_PLAIN));
+    DAWN_TRY(c.gemm(p, EPI_PLAIN, PC_OUTPROJ));
   }
   return tap(c, name, dst);
 }
@@ -447,21 +516,23 @@ int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const st
 int mid_spatial_attn(Ctx& c, const AttnW& w, const Act& x, const std::string& name) {
   dawn_unet* h = c.h;
   const int F = h->F, P = x.H * x.W, M = F * P;
-  h->launches++;
-  DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
+  {
+    ProfScope ps(c, PC_ROWSTATS, 0, 4.0 * M * x.C);
+    DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
+  }
   {
     GemmParams p; base_params(p, x, F);
     p.B = w.Wqkv; p.ldb = 768; p.N = 768; p.K = x.C;
     p.rowstats = h->ROWSTATS; p.wsum = w.wsum;
     p.Out = h->QKV; p.ldo = 768;
-    DAWN_TRY(c.gemm(p, EPI_QKV_MID));
+    DAWN_TRY(c.gemm(p, EPI_QKV_MID, PC_QKV));
   }
   {
     AttnArgs a{};
     a.qkv = h->QKV; a.ld = 768; a.out = h->O; a.ldo = 256;
     a.nseq = F; a.L = P; a.seq_base_stride = P; a.elem_stride = 1;
     a.band = 1 << 30; a.bias = nullptr; a.q_lo = 0; a.q_hi = P;
-    h->launches++;
+    ProfScope ps(c, PC_ATTN_CORE, 4.0 * 32 * 8 * (double)F * P * P, 4.0 * M * 1024);
     DAWN_TRY(launch_attention(a, c.st));
   }
   {
@@ -469,7 +540,7 @@ int mid_spatial_attn(Ctx& c, const AttnW& w, const Act& x, const std::string& na
     GemmParams p; base_params(p, o, F);
     set_weights(p, w.out);
     p.Res = x.p; p.ldr = x.ld; p.Out = x.p; p.ldo = x.ld;
-    DAWN_TRY(c.gemm(p, EPI_PLAIN));
+    DAWN_TRY(c.gemm(p, EPI_PLAIN, PC_OUTPROJ));
   }
   return tap(c, name, x);
 }
@@ -478,25 +549,29 @@ int mid_spatial_attn(Ctx& c, const AttnW& w, const Act& x, const std::string& na
 int sla(Ctx& c, const SlaW& w, const Act& x, const std::string& name) {
   dawn_unet* h = c.h;
   const int F = h->F, P = x.H * x.W, M = F * P;
-  h->launches++;
-  DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
+  {
+    ProfScope ps(c, PC_ROWSTATS, 0, 4.0 * M * x.C);
+    DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
+  }
   {
     GemmParams p; base_params(p, x, F);
     p.B = w.Wqkv; p.ldb = 768; p.N = 768; p.K = x.C;
     p.rowstats = h->ROWSTATS; p.wsum = w.wsum; p.q_post_scale = 1.0f / sqrtf(32.0f);
     p.Out = h->QKV; p.ldo = 768;
-    DAWN_TRY(c.gemm(p, EPI_QKV_SLA));
+    DAWN_TRY(c.gemm(p, EPI_QKV_SLA, PC_QKV));
   }
   const int ldb = round_up(x.C, 64);
-  h->launches++;
-  DAWN_TRY(launch_sla_context(h->QKV, 768, F, P, w.WoutT, x.C, h->BF, ldb, c.st));
+  {
+    ProfScope ps(c, PC_SLA_CTX, 2.0 * 8 * 32 * 32 * M + 2.0 * F * 256 * 32 * x.C, 4.0 * M * 768);
+    DAWN_TRY(launch_sla_context(h->QKV, 768, F, P, w.WoutT, x.C, h->BF, ldb, c.st));
+  }
   {
     Act q{h->QKV, 768, 256, x.H, x.W};
     GemmParams p; base_params(p, q, F);
     p.B = h->BF; p.ldb = ldb; p.b_batch_stride = (long long)256 * ldb; p.N = x.C; p.K = 256;
     p.rows_per_batch = P; p.bias = w.bout;
     p.Res = x.p; p.ldr = x.ld; p.Out = x.p; p.ldo = x.ld;
-    DAWN_TRY(c.gemm(p, EPI_PLAIN));
+    DAWN_TRY(c.gemm(p, EPI_PLAIN, PC_OUTPROJ));
   }
   return tap(c, name, x);
 }
@@ -511,7 +586,7 @@ int downsample(Ctx& c, const ConvW& w, const Act& x, const Act& out, const std::
   p.M = c.h->F * out.H * out.W; p.rows_per_batch = p.M;
   p.OH = out.H; p.OW = out.W; p.P = out.H * out.W;
   p.Out = out.p; p.ldo = out.ld;
-  DAWN_TRY(c.gemm(p, EPI_PLAIN));
+  DAWN_TRY(c.gemm(p, EPI_PLAIN, PC_CONV_OTHER));
   return tap(c, name, out);
 }
 
@@ -525,7 +600,7 @@ int upsample(Ctx& c, const UpW& u, const Act& x, const Act& out, const std::stri
         for (int tx = 0; tx < 2; ++tx) { p.dy[ty * 2 + tx] = (signed char)kUpD[py][ty]; p.dx[ty * 2 + tx] = (signed char)kUpD[px][tx]; }
       p.OH = out.H; p.OW = out.W; p.out_stride = 2; p.oy0 = py; p.ox0 = px;
       p.Out = out.p; p.ldo = out.ld;
-      DAWN_TRY(c.gemm(p, EPI_PLAIN));
+      DAWN_TRY(c.gemm(p, EPI_PLAIN, PC_CONV_OTHER));
     }
   return tap(c, name, out);
 }
@@ -549,12 +624,14 @@ int tap(Ctx& c, const std::string& name, const Act& a) {
 // ------------------------------------------------------------------------------------------ per-clip tables
 int prep_cond(dawn_unet* h, const float* cond, cudaStream_t st) {
   const int F = h->F;
+  Ctx c{h, st};
   const int off[3] = {h->cfg.cond_aud, 0, h->cfg.cond_aud + h->cfg.cond_pose};          // pose, aud, eye slices (U:425-428)
   const int kd[3] = {h->cfg.cond_pose, h->cfg.cond_aud, h->cfg.cond_eye};
   for (auto& r : h->rb) {
     if (!r.cond) continue;
     for (int a = 0; a < 3; ++a) {
-      h->launches += 3;
+      ProfScope ps(c, PC_PREP, 0, 0);
+      h->launches += 2;
       DAWN_TRY(launch_cond_mlp(cond, h->cond_dim, off[a], kd[a], r.mW[a], r.mB[a], 2 * r.co, F, h->CTX, st));
       DAWN_TRY(launch_linear_nobias(h->CTX, 2 * r.co, r.ca[a].Wkv, 128, F, h->KV, st));
       CaTableArgs t{};
@@ -570,9 +647,12 @@ int forward_core(dawn_unet* h, const int64_t* t_dev, float* out, cudaStream_t st
   Ctx c{h, st};
   const int F = h->F, nlev = h->nlev, dim = h->cfg.dim;
   DAWN_CUDA_OK(cudaMemsetAsync(h->STATS, 0, sizeof(double) * 16 * h->n_stats, st));
-  h->launches += 2;
-  DAWN_TRY(launch_time_mlp(t_dev, h->time_freqs, dim, h->tW1, h->tb1, h->tW2, h->tb2, h->TSILU, st));
-  DAWN_TRY(launch_film(h->film_descs, h->n_film, h->TSILU, h->tdim, st));
+  {
+    ProfScope ps(c, PC_MISC, 0, 0);
+    h->launches += 1;
+    DAWN_TRY(launch_time_mlp(t_dev, h->time_freqs, dim, h->tW1, h->tb1, h->tW2, h->tb2, h->TSILU, st));
+    DAWN_TRY(launch_film(h->film_descs, h->n_film, h->TSILU, h->tdim, st));
+  }
 
   const int H0 = h->lH[0], W0 = h->lW[0];
   Act r{h->XR + dim, 2 * dim, dim, H0, W0};            // init conv output lives in the second half of cat(x, r) (U:911, 955)
@@ -630,7 +710,7 @@ int forward_core(dawn_unet* h, const int64_t* t_dev, float* out, cudaStream_t st
   Act hf{h->HF, dim, dim, H0, W0}, ho{h->HO, dim, dim, H0, W0};
   DAWN_TRY(resblock(c, h->rb[h->rb_index["final_conv.0"]], xr, hf));
   DAWN_TRY(resblock(c, h->rb[h->rb_index["occlusion_map.0"]], xr, ho));
-  h->launches++;
+  ProfScope ps(c, PC_MISC, 0, 4.0 * F * H0 * W0 * (2 * dim + 3));
   DAWN_TRY(launch_heads_out(h->HF, h->HO, dim, F * H0 * W0, h->headW[0], h->headB[0], h->cfg.out_grid_dim,
                             h->headW[1], h->headB[1], h->cfg.out_conf_dim, out, st));
   return 0;
@@ -669,6 +749,7 @@ int dawn_unet_create(const dawn_unet_cfg* cfg, dawn_unet** out) {
 
 void dawn_unet_destroy(dawn_unet* h) {
   if (!h) return;
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   free_all(h->owned);
   free_all(h->ws_owned);
   delete h;
@@ -841,14 +922,16 @@ int dawn_unet_set_clip_invariants(dawn_unet* h, const float* fea, const float* c
   Ctx c{h, st};
   const int H0 = h->lH[0], W0 = h->lW[0], dim = h->cfg.dim, k = h->cfg.init_kernel_size;
   // per-clip constant part of the init conv: conv(cat[0, fea]) + bias  (linearity)
-  h->launches++;
-  DAWN_TRY(launch_ncf_to_nhwc(fea, h->cfg.channels - 3, 1, H0 * W0, h->cin_pad, 3, h->FEA288, st));
+  {
+    ProfScope ps(c, PC_PREP, 0, 0);
+    DAWN_TRY(launch_ncf_to_nhwc(fea, h->cfg.channels - 3, 1, H0 * W0, h->cin_pad, 3, h->FEA288, st));
+  }
   {
     Act in{h->FEA288, h->cin_pad, h->cin_pad, H0, W0};
     GemmParams p; base_params(p, in, 1);
     set_weights(p, h->init_full); set_square_taps(p, k, k / 2);
     p.Out = h->MAP; p.ldo = dim;
-    DAWN_TRY(c.gemm(p, EPI_PLAIN));
+    DAWN_TRY(c.gemm(p, EPI_PLAIN, PC_PREP));
   }
   DAWN_TRY(prep_cond(h, cond, st));
   h->have_invariants = true;
@@ -864,14 +947,16 @@ int dawn_unet_forward(dawn_unet* h, const float* x, const int64_t* t, const floa
   const int H0 = h->lH[0], W0 = h->lW[0], dim = h->cfg.dim, k = h->cfg.init_kernel_size;
   DAWN_TRY(prep_cond(h, cond, st));
   h->have_invariants = false;         // MAP not refreshed by this entry
-  h->launches++;
-  DAWN_TRY(launch_ncf_to_nhwc(x, h->cfg.channels, h->F, H0 * W0, h->cin_pad, 0, h->X288, st));
+  {
+    ProfScope ps(c, PC_MISC, 0, 8.0 * h->F * H0 * W0 * h->cin_pad);
+    DAWN_TRY(launch_ncf_to_nhwc(x, h->cfg.channels, h->F, H0 * W0, h->cin_pad, 0, h->X288, st));
+  }
   {
     Act in{h->X288, h->cin_pad, h->cin_pad, H0, W0};
     GemmParams p; base_params(p, in, h->F);
     set_weights(p, h->init_full); set_square_taps(p, k, k / 2);
     p.Out = h->XR + dim; p.ldo = 2 * dim;
-    DAWN_TRY(c.gemm(p, EPI_PLAIN));
+    DAWN_TRY(c.gemm(p, EPI_PLAIN, PC_CONV_OTHER));
   }
   return forward_core(h, t, out, st);
 }
@@ -882,9 +967,13 @@ int dawn_unet_forward_x3(dawn_unet* h, const float* x_t, const int64_t* t, float
   cudaStream_t st = (cudaStream_t)stream;
   h->launches = 0;
   const int H0 = h->lH[0], W0 = h->lW[0], dim = h->cfg.dim;
-  h->launches++;
-  DAWN_TRY(launch_init_conv_x3(x_t, h->F, H0, W0, h->init_w3, h->MAP, dim, h->XR + dim, 2 * dim,
-                               h->cfg.init_kernel_size, st));
+  {
+    Ctx c{h, st};
+    const double k2 = (double)h->cfg.init_kernel_size * h->cfg.init_kernel_size;
+    ProfScope ps(c, PC_MISC, 2.0 * h->F * H0 * W0 * dim * 3 * k2, 4.0 * h->F * H0 * W0 * (dim + 3));
+    DAWN_TRY(launch_init_conv_x3(x_t, h->F, H0, W0, h->init_w3, h->MAP, dim, h->XR + dim, 2 * dim,
+                                 h->cfg.init_kernel_size, st));
+  }
   return forward_core(h, t, out, st);
 }
 
@@ -935,6 +1024,32 @@ int dawn_unet_set_tap(dawn_unet* h, const char* name, float* dst) {
 }
 
 int64_t dawn_unet_last_launch_count(dawn_unet* h) { return h ? h->launches : 0; }
+
+int dawn_unet_profile_enable(dawn_unet* h, int on) {
+  DAWN_CHECK(h, "null handle");
+  h->prof_on = on != 0;
+  h->prof_used = 0;
+  h->prof_recs.clear();
+  for (int i = 0; i < DAWN_PROF_NCAT; ++i) { h->prof_ms[i] = 0; h->prof_flops[i] = 0; h->prof_bytes[i] = 0; h->prof_cnt[i] = 0; }
+  return 0;
+}
+
+int dawn_unet_profile_read(dawn_unet* h, double* ms, double* flops, double* bytes, int64_t* count) {
+  DAWN_CHECK(h && ms && flops && bytes && count, "null argument");
+  if (h->prof_used > 0) {
+    DAWN_CUDA_OK(cudaEventSynchronize(h->prof_ev[h->prof_used - 1]));
+    for (size_t i = 0; i < h->prof_recs.size(); ++i) {
+      float t = 0.f;
+      DAWN_CUDA_OK(cudaEventElapsedTime(&t, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+      const auto& r = h->prof_recs[i];
+      h->prof_ms[r.cat] += t; h->prof_flops[r.cat] += r.flops; h->prof_bytes[r.cat] += r.bytes; h->prof_cnt[r.cat]++;
+    }
+    h->prof_used = 0;
+    h->prof_recs.clear();
+  }
+  for (int i = 0; i < DAWN_PROF_NCAT; ++i) { ms[i] = h->prof_ms[i]; flops[i] = h->prof_flops[i]; bytes[i] = h->prof_bytes[i]; count[i] = h->prof_cnt[i]; }
+  return 0;
+}
 int64_t dawn_unet_workspace_bytes(dawn_unet* h) { return h ? h->ws_bytes : 0; }
 
 }  // extern "C"

@@ -378,6 +378,17 @@ class Unet3D(nn.Module):
             lib.dawn_unet_set_tap(self._handle, n.encode(), None)
         self._tap_bufs = {}
 
+    def profile(self, on=True):
+        check(lib.dawn_unet_profile_enable(self._handle, 1 if on else 0), "dawn_unet_profile_enable")
+
+    def profile_read(self):
+        """{category: dict(ms, flops, bytes, count)} accumulated since profile(True)."""
+        n = _lib.PROF_NCAT
+        ms, fl, by = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_double * n)()
+        cnt = (ctypes.c_int64 * n)()
+        check(lib.dawn_unet_profile_read(self._handle, ms, fl, by, cnt), "dawn_unet_profile_read")
+        return {c: dict(ms=ms[i], flops=fl[i], bytes=by[i], count=int(cnt[i])) for i, c in enumerate(_lib.PROF_CATS)}
+
     def last_launch_count(self):
         return int(lib.dawn_unet_last_launch_count(self._handle)) if self._handle is not None else 0
 

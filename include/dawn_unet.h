@@ -81,6 +81,16 @@ int dawn_unet_set_tap(dawn_unet* h, const char* name, float* dst);
 /* channels and spatial size of a tap for the current set_num_frames: writes C, h_l, w_l */
 int dawn_unet_tap_shape(dawn_unet* h, const char* name, int* C, int* hl, int* wl);
 
+/* Per-kernel-category timing with CUDA events on the launching stream (bench.py's roofline object).
+ * enable(1) clears the counters and brackets every launch of the following forward calls with events;
+ * read() synchronises on the last event and returns, per category, accumulated milliseconds, algorithmic
+ * flops (2*MAC, counted once — not the 3 split-precision passes), algorithmic bytes and launch counts.
+ * Arrays must hold DAWN_PROF_NCAT entries.  Category order: conv3x3, conv_other, qkv_proj, out_proj,
+ * ca_gate, gn_hcond, attn_core, sla_context, gn_apply, rowstats, ca_rstd, misc, prep. */
+#define DAWN_PROF_NCAT 16
+int dawn_unet_profile_enable(dawn_unet* h, int on);
+int dawn_unet_profile_read(dawn_unet* h, double* ms, double* flops, double* bytes, int64_t* count);
+
 /* number of kernels launched by the last forward on this handle (bench.py's gpu_launches) */
 int64_t dawn_unet_last_launch_count(dawn_unet* h);
 /* bytes of device workspace currently held */
