@@ -85,6 +85,33 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def log(msg):
+    print(f"[bench +{time.perf_counter() - T_START:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+T_START = time.perf_counter()
+
+
+def host_threads():
+    """CPU threads this process may really use: min(affinity, cgroup quota); os.cpu_count() alone can be the
+    whole host and oversubscribing a quota-limited container makes OpenMP crawl."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            q, per = f.read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, min(n, 64))
+
+
 def synth_clip(seed):
     g = torch.Generator().manual_seed(seed)
     x_t = torch.randn(3, F_CLIP, H_LAT, W_LAT, generator=g)
@@ -98,8 +125,9 @@ def cpu_baseline_run(state_dict, steps, warmup):
     travel to this box).  Bounded sample: the first CPU_SAMPLE_FRAMES frames of the same 64x64-latent workload;
     per-frame cost is scaled to the 200-frame clip."""
     from oracle import unet_oracle as O
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
+    log(f"cpu baseline: oracle port on {cores} threads, {CPU_SAMPLE_FRAMES} frames sample")
     x_t, fea, cond = synth_clip(1)
     Fs = CPU_SAMPLE_FRAMES
     x = torch.cat([x_t[:, :Fs], fea.unsqueeze(1).expand(-1, Fs, -1, -1)], dim=0)[None].contiguous()
@@ -111,6 +139,7 @@ def cpu_baseline_run(state_dict, steps, warmup):
         for i in range(warmup + steps):
             t0 = time.perf_counter()
             O.unet_forward(state_dict, cfg, x, t, c)
+            log(f"  cpu forward {i}: {time.perf_counter() - t0:.2f} s")
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     sec = statistics.median(times)
@@ -126,6 +155,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-worker", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -140,6 +170,10 @@ def main():
               "frames": F_CLIP, "latent": [H_LAT, W_LAT], "parallelism": f"replicas x{args.gpus} (one 200-frame clip per GPU)" if args.gpus > 1 else "single GPU",
               "l2": "per-step working set ~7 GB >> 126 MB L2 (inputs larger than L2, no explicit flush)"}
 
+    if args.cpu_baseline_worker:
+        cb, _ = cpu_baseline_run(sd_cpu, 3, 1)
+        print(json.dumps(cb))
+        return
     if args.impl == "reference":
         if rank != 0:
             return
@@ -168,6 +202,7 @@ def main():
     t_d = torch.full((1,), 500, dtype=torch.long, device=dev)
     out_d = torch.empty((3, F_CLIP, H_LAT, W_LAT), device=dev)
     net.set_clip_invariants(fea_d, cond_d)
+    log("module ready, clip invariants set")
 
     def barrier():
         torch.cuda.synchronize()
@@ -200,6 +235,7 @@ def main():
         ms_total = float(tt.item())
     ms_per_step = ms_total / args.steps
     value = args.gpus * 1000.0 / ms_per_step
+    log(f"device-resident: {ms_per_step:.2f} ms/step")
 
     # ---------------- end to end through the C-ABI with HOST buffers (H2D inputs + D2H eps every step)
     xt_h, fea_h, cond_h = x_t.pin_memory(), fea.pin_memory(), cond.pin_memory()
@@ -216,6 +252,7 @@ def main():
         tt = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
+    log(f"e2e: {e2e_s / args.steps * 1e3:.2f} ms/step")
     h2d = (xt_h.numel() + fea_h.numel() + cond_h.numel()) * 4 + 8
     d2h = out_h.numel() * 4
     e2e = {"value": args.gpus * args.steps / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -248,7 +285,15 @@ def main():
 
     cpu_baseline = None
     if args.gpus == 1 and not args.no_cpu_baseline:
-        cpu_baseline, _ = cpu_baseline_run(sd_cpu, 3, 1)
+        # time-boxed child process: a slow or wedged host must not take the GPU numbers down with it
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-worker"], capture_output=True,
+                               text=True, timeout=240)
+            cpu_baseline = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:  # noqa: BLE001
+            cpu_baseline = {"value": None, "unit": "steps/s", "cores": host_threads(), "kind": "port",
+                            "sample": f"not measured: {type(e).__name__}"}
+        log(f"cpu baseline: {cpu_baseline}")
 
     line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
