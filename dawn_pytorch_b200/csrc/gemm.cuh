@@ -28,6 +28,7 @@ struct GemmParams {
   int rows_per_batch;      // rows sharing one B matrix (P for per-frame weights, else M)
   // B operand [K][ldb] (ldb multiple of 64, zero padded)
   const float* B; int ldb; long long b_batch_stride;
+  const float* Bimg;       // optional tcgen05 image of B (tc_pack_weights), or null
   // output
   float* Out; int ldo; int OH, OW, out_stride, oy0, ox0;
   const float* bias;

@@ -1,0 +1,456 @@
+// tcgen05 implicit GEMM for the DAWN UNet contractions (sm_100a): Out = epilogue(A (gathered, fp32) x B (weights)).
+//
+//   * 128-row position tile x 64-column output tile, K streamed in 32-float panels (= one 128-byte swizzle row).
+//   * fp32-level parity needs the 3-term split  hi*hi + hi*lo + lo*hi   -> kind::tf32 MMAs on
+//     (A_lo,B_hi), (A_hi,B_lo), (A_hi,B_hi); A is split on the fly by the producer warps, B is pre-split and
+//     pre-swizzled on the host into ready-to-copy shared-memory images (1-D bulk copies, no tensor maps).
+//   * The tensor core adds into its accumulator with round-toward-zero; chained over a long K that is a biased
+//     error (measured 1.4e-4 at K=14112).  So TMEM holds TWO accumulator buffers; every CHUNK panels the issuer
+//     flips buffers (first MMA overwrites) and the epilogue warps drain the finished buffer into fp32 registers
+//     with ordinary round-to-nearest adds while the next chunk is already being multiplied.
+//   * persistent CTAs, warp roles: 0-3 A producers (gather + split + swizzled st.shared), 4-7 accumulate/epilogue
+//     (each thread owns one output row), 8 MMA issuer (one elected thread), 9 weight loader (one elected thread).
+#include "common.cuh"
+#include "gemm.cuh"
+#include "tc_gemm.cuh"
+
+namespace dawn {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 64;
+constexpr int BKP = 32;                 // floats per panel row (128 bytes)
+constexpr int STAGES = 4;
+constexpr int CHUNK = 4;                // panels accumulated inside TMEM before a drain (K = 128)
+constexpr int A_PANEL = BM * 128;       // 16 KB
+constexpr int B_PANEL = BN * 128;       // 8 KB
+constexpr int STAGE_BYTES = 2 * A_PANEL + 2 * B_PANEL;     // A_hi, A_lo, B_hi, B_lo = 48 KB
+constexpr int NTHREADS = 320;
+constexpr int TMEM_COLS = 2 * BN;       // two accumulator buffers
+constexpr int SMEM_DYN = STAGES * STAGE_BYTES + 1024;      // + alignment slack
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte-swizzled operand panel: rows of 128 B, 8-row atoms of 1024 B (SBO), descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// byte offset of 16-byte chunk c (0..7) of row r inside a swizzled panel
+__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
+
+struct RowInfo { int pix; short iy, ix; };     // per tile row: input frame base pixel, top-left input coordinate
+
+template <int EPI>
+__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p, const float* __restrict__ Bimg, int KC,
+                                                              int tiles_m, int tiles_n) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t a_full[STAGES], b_full[STAGES], slot_free[STAGES], acc_full[2], acc_free[2];
+  __shared__ uint32_t s_tmem_base;
+  __shared__ RowInfo s_rows[2][BM];
+  __shared__ float s_stat[16];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&a_full[s], 128); mbar_init(&b_full[s], 1); mbar_init(&slot_free[s], 1); }
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_free[0], 128); mbar_init(&acc_free[1], 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  const int total_tiles = tiles_m * tiles_n;
+  const int Ps = p.OHs * p.OWs;
+  const int chunks_per_tap = p.Cin / BKP;
+
+  if (warp < 4) {
+    // =============================================================== A producers
+    const int c16 = tid & 7;            // 16-byte chunk inside the 128-byte row
+    const int r0 = tid >> 3;            // rows r0 + 16 q
+    uint32_t it = 0;
+    int tile_iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+      const int m0 = (tile / tiles_n) * BM;
+      RowInfo* rows = s_rows[tile_iter & 1];
+      // row table for this tile (double-buffered across tiles; synchronised among the 128 producers only)
+      {
+        const int m = m0 + tid;
+        RowInfo ri;
+        if (m < p.M) {
+          const int f = m / Ps, rem = m - f * Ps;
+          const int i = rem / p.OWs, j = rem - i * p.OWs;
+          ri.pix = f * p.IH * p.IW; ri.iy = (short)(i * p.in_stride); ri.ix = (short)(j * p.in_stride);
+        } else {
+          ri.pix = -1; ri.iy = 0; ri.ix = 0;
+        }
+        rows[tid] = ri;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int kc = 0; kc < KC; ++kc, ++it) {
+        const int s = it % STAGES;
+        const uint32_t round = it / STAGES;
+        const int tap = kc / chunks_per_tap;
+        const int c0 = (kc - tap * chunks_per_tap) * BKP;
+        const int dy = p.dy[tap], dx = p.dx[tap];
+        float4 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const RowInfo ri = rows[r0 + 16 * q];
+          const int iy = ri.iy + dy, ix = ri.ix + dx;
+          const bool ok = (ri.pix >= 0) && (iy >= 0) && (iy < p.IH) && (ix >= 0) && (ix < p.IW);
+          v[q] = ok ? __ldg(reinterpret_cast<const float4*>(p.A + (size_t)(ri.pix + iy * p.IW + ix) * p.lda + c0) + c16)
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        mbar_wait(&slot_free[s], (round & 1) ^ 1);
+        uint8_t* a_hi = smem + s * STAGE_BYTES;
+        uint8_t* a_lo = a_hi + A_PANEL;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+          split_tf32(v[q].x, h0, l0); split_tf32(v[q].y, h1, l1); split_tf32(v[q].z, h2, l2); split_tf32(v[q].w, h3, l3);
+          const uint32_t off = swz(r0 + 16 * q, c16);
+          *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h0, h1, h2, h3);
+          *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l0, l1, l2, l3);
+        }
+        fence_proxy_async();
+        mbar_arrive(&a_full[s]);
+      }
+    }
+  } else if (warp == 9) {
+    // =============================================================== weight loader (pre-swizzled hi|lo images)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % tiles_n;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(Bimg) + (size_t)nt * KC * (2 * B_PANEL);
+        for (int kc = 0; kc < KC; ++kc, ++it) {
+          const int s = it % STAGES;
+          const uint32_t round = it / STAGES;
+          mbar_wait(&slot_free[s], (round & 1) ^ 1);
+          mbar_arrive_expect_tx(&b_full[s], 2 * B_PANEL);
+          bulk_copy_g2s(smem + s * STAGE_BYTES + 2 * A_PANEL, src + (size_t)kc * (2 * B_PANEL), 2 * B_PANEL, &b_full[s]);
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      uint32_t it = 0, cg = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < KC; ++kc, ++it) {
+          const int s = it % STAGES;
+          const uint32_t round = it / STAGES;
+          const bool chunk_first = (kc % CHUNK) == 0;
+          const bool chunk_last = ((kc % CHUNK) == CHUNK - 1) || (kc == KC - 1);
+          const uint32_t buf = cg & 1;
+          if (chunk_first) {
+            mbar_wait(&acc_free[buf], ((cg >> 1) & 1) ^ 1);
+            tc_fence_after();
+          }
+          mbar_wait(&a_full[s], round & 1);
+          mbar_wait(&b_full[s], round & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t ahi = make_desc(sa), alo = make_desc(sa + A_PANEL);
+          const uint64_t bhi = make_desc(sa + 2 * A_PANEL), blo = make_desc(sa + 2 * A_PANEL + B_PANEL);
+          const uint32_t d = tmem_base + buf * BN;
+#pragma unroll
+          for (int j = 0; j < BKP / 8; ++j) {
+            const uint64_t o = (uint64_t)(j * 2);               // +32 bytes per k-step, in 16-byte units
+            tc_mma_tf32(d, alo + o, bhi + o, idesc, (chunk_first && j == 0) ? 0u : 1u);
+            tc_mma_tf32(d, ahi + o, blo + o, idesc, 1u);
+            tc_mma_tf32(d, ahi + o, bhi + o, idesc, 1u);
+          }
+          tc_commit(&slot_free[s]);
+          if (chunk_last) { tc_commit(&acc_full[buf]); ++cg; }
+        }
+      }
+    }
+  } else {
+    // =============================================================== accumulate + epilogue (warps 4..7)
+    const int ew = warp - 4;                              // == warp % 4 -> TMEM lanes 32*ew .. 32*ew+31
+    const int row_in_tile = ew * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
+    const int etid = tid - 128;
+    uint32_t cg = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      float acc[BN];
+#pragma unroll
+      for (int i = 0; i < BN; ++i) acc[i] = 0.f;
+      const int nchunks = (KC + CHUNK - 1) / CHUNK;
+      for (int c = 0; c < nchunks; ++c, ++cg) {
+        const uint32_t buf = cg & 1;
+        mbar_wait(&acc_full[buf], (cg >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int hlf = 0; hlf < BN / 32; ++hlf) {
+          float v[32];
+          tmem_ld32(tmem_base + lane_addr + buf * BN + hlf * 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[hlf * 32 + i] += v[i];
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_free[buf]);
+      }
+
+      // ---------------------------------------------------------- final epilogue: this thread owns row m
+      const int m = m0 + row_in_tile;
+      const bool rv = m < p.M;
+      const int mc = rv ? m : (p.M - 1);
+      const int f = mc / Ps, rem = mc - f * Ps;
+      const int oi = rem / p.OWs, oj = rem - oi * p.OWs;
+      const size_t opix = (size_t)(f * p.OH + oi * p.out_stride + p.oy0) * p.OW + oj * p.out_stride + p.ox0;
+
+      if (EPI == EPI_PLAIN) {
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < BN; ++i) acc[i] += p.bias[n0 + i];
+        }
+        if (rv && p.Res) {
+          const float4* rp = reinterpret_cast<const float4*>(p.Res + opix * p.ldr + n0);
+#pragma unroll
+          for (int i = 0; i < BN / 4; ++i) {
+            const float4 r = rp[i];
+            acc[4 * i] += r.x; acc[4 * i + 1] += r.y; acc[4 * i + 2] += r.z; acc[4 * i + 3] += r.w;
+          }
+        }
+        if (rv) {
+          float4* op = reinterpret_cast<float4*>(p.Out + opix * p.ldo + n0);
+#pragma unroll
+          for (int i = 0; i < BN / 4; ++i) op[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+        }
+        if (p.stats != nullptr) {
+          // GroupNorm partial statistics (U:230): per 8-column sub-block, reduced over the warp's 32 rows
+          if (etid < 16) s_stat[etid] = 0.f;
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll
+          for (int b8 = 0; b8 < BN / 8; ++b8) {
+            float s = 0.f, ss = 0.f;
+            if (rv) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { const float x = acc[b8 * 8 + i]; s += x; ss += x * x; }
+            }
+            s = warp_sum(s); ss = warp_sum(ss);
+            if (lane == 0) {
+              const int grp = (n0 + b8 * 8) / p.cpg;
+              atomicAdd(&s_stat[2 * grp], s);
+              atomicAdd(&s_stat[2 * grp + 1], ss);
+            }
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (etid < 16) {
+            const int grp = etid >> 1;
+            const int glo = n0 / p.cpg, ghi = (n0 + BN - 1) / p.cpg;
+            if (grp >= glo && grp <= ghi) atomicAdd(&p.stats[etid], (double)s_stat[etid]);
+          }
+        }
+      } else {
+        // LayerNorm fold (see gemm.cu): v = rstd * (acc - mu * colsum)
+        const float mu = p.rowstats[2 * (size_t)mc], rs = p.rowstats[2 * (size_t)mc + 1];
+#pragma unroll
+        for (int i = 0; i < BN; ++i) acc[i] = rs * (acc[i] - mu * p.wsum[n0 + i]);
+        if (EPI == EPI_QKV_TEMPORAL) {
+          if (n0 < 512) {
+            const int fr = mc / p.P;
+#pragma unroll
+            for (int i = 0; i < BN; i += 2) {
+              const int pi = ((n0 + i) & 31) >> 1;
+              const float2 cs = *reinterpret_cast<const float2*>(p.rot + (size_t)(fr * 16 + pi) * 2);
+              const float x0 = acc[i], x1 = acc[i + 1];
+              acc[i] = x0 * cs.x - x1 * cs.y;
+              acc[i + 1] = x1 * cs.x + x0 * cs.y;
+            }
+          }
+        } else if (EPI == EPI_QKV_SLA) {
+          if (n0 < 256) {
+#pragma unroll
+            for (int hd = 0; hd < BN / 32; ++hd) {
+              float mx = acc[hd * 32];
+#pragma unroll
+              for (int i = 1; i < 32; ++i) mx = fmaxf(mx, acc[hd * 32 + i]);
+              float sum = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) { acc[hd * 32 + i] = expf(acc[hd * 32 + i] - mx); sum += acc[hd * 32 + i]; }
+              const float inv = p.q_post_scale / sum;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) acc[hd * 32 + i] *= inv;
+            }
+          }
+        }
+        if (EPI == EPI_CA_GATE) {
+          const int fr = mc / p.P;
+          const int ca = n0 >> 6;
+          const float* kq = p.kq + ((size_t)fr * 3 + ca) * 64;
+          const float* nk = p.nkq + ca * 8;
+#pragma unroll
+          for (int hd = 0; hd < 8; ++hd) {
+            float nrm2 = 0.f, dr = 0.f, dn = 0.f;
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+              const float q = acc[hd * 8 + d];
+              nrm2 += q * q; dr += q * kq[hd * 8 + d]; dn += q * nk[d];
+            }
+            const float inv = 8.0f / fmaxf(sqrtf(nrm2), 1e-12f);
+            const float sr = dr * inv, sn = dn * inv;
+            const float mx = fmaxf(sr, sn);
+            const float er = expf(sr - mx), en = expf(sn - mx);
+            if (rv) p.gates[(size_t)m * 24 + ca * 8 + hd] = er / (er + en);
+          }
+        } else if (rv) {
+          float4* op = reinterpret_cast<float4*>(p.Out + opix * p.ldo + n0);
+#pragma unroll
+          for (int i = 0; i < BN / 4; ++i) op[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+template <int EPI>
+int launch_t(const GemmParams& p, const float* Bimg, cudaStream_t st) {
+  static bool attr_set = false;
+  static int num_sms = 0;
+  if (!attr_set) {
+    DAWN_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
+    int dev = 0;
+    DAWN_CUDA_OK(cudaGetDevice(&dev));
+    DAWN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_set = true;
+  }
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = p.N / BN;
+  const int KC = p.K / BKP;
+  const int grid = std::min(tiles_m * tiles_n, num_sms);
+  tc_gemm_kernel<EPI><<<grid, NTHREADS, SMEM_DYN, st>>>(p, Bimg, KC, tiles_m, tiles_n);
+  DAWN_LAUNCH_OK();
+  return 0;
+}
+
+inline uint32_t tf32_rna(float x) {       // cvt.rna.tf32.f32 on the host: nearest, ties away from zero
+  uint32_t u; memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  return u;
+}
+
+}  // namespace
+
+bool tc_gemm_supported(const GemmParams& p, int epi) {
+  if (epi == EPI_GN_APPLY) return false;
+  if (p.b_batch_stride != 0 || p.rows_per_batch != p.M) return false;
+  if (p.N % BN != 0 || p.K % BKP != 0 || p.Cin % BKP != 0) return false;
+  if ((p.lda & 3) || (p.ldo & 3) || (p.Res && (p.ldr & 3))) return false;
+  if (p.M < BM) return false;
+  if (epi == EPI_PLAIN && p.stats && (p.cpg % 8 != 0)) return false;
+  return true;
+}
+
+// Host: [K][ldb] fp32 weights -> per (n-tile, k-panel) shared-memory images: hi panel (64 x 128 B, swizzled) | lo panel
+size_t tc_pack_weights(const float* Bkn, int K, int N, int ldb, std::vector<float>& out) {
+  const int KC = K / BKP, NT = N / BN;
+  out.assign((size_t)NT * KC * 2 * (B_PANEL / 4), 0.f);
+  for (int nt = 0; nt < NT; ++nt)
+    for (int kc = 0; kc < KC; ++kc) {
+      uint32_t* hi = reinterpret_cast<uint32_t*>(out.data()) + ((size_t)nt * KC + kc) * 2 * (B_PANEL / 4);
+      uint32_t* lo = hi + B_PANEL / 4;
+      for (int n = 0; n < BN; ++n)
+        for (int k = 0; k < BKP; ++k) {
+          const float w = Bkn[(size_t)(kc * BKP + k) * ldb + nt * BN + n];
+          const uint32_t h = tf32_rna(w);
+          float hf; memcpy(&hf, &h, 4);
+          const uint32_t l = tf32_rna(w - hf);
+          const int off = (n >> 3) * 256 + (n & 7) * 32 + (((k >> 2) ^ (n & 7)) << 2) + (k & 3);   // in 4-byte words
+          hi[off] = h; lo[off] = l;
+        }
+    }
+  return out.size();
+}
+
+int launch_tc_gemm(const GemmParams& p, const float* Bimg, int epi, cudaStream_t st) {
+  if (!tc_gemm_supported(p, epi)) { set_last_error("launch_tc_gemm: unsupported geometry"); return -1; }
+  switch (epi) {
+    case EPI_PLAIN: return launch_t<EPI_PLAIN>(p, Bimg, st);
+    case EPI_QKV_TEMPORAL: return launch_t<EPI_QKV_TEMPORAL>(p, Bimg, st);
+    case EPI_QKV_SLA: return launch_t<EPI_QKV_SLA>(p, Bimg, st);
+    case EPI_QKV_MID: return launch_t<EPI_QKV_MID>(p, Bimg, st);
+    case EPI_CA_GATE: return launch_t<EPI_CA_GATE>(p, Bimg, st);
+  }
+  set_last_error("launch_tc_gemm: bad epilogue id");
+  return -1;
+}
+
+}  // namespace dawn

@@ -1,0 +1,15 @@
+// tcgen05 (5th-gen tensor core, TMEM accumulators) implicit GEMM — see tc_gemm.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <vector>
+#include "gemm.cuh"
+
+namespace dawn {
+
+// true when launch_tc_gemm can run this problem (regular shapes, static weights); otherwise use launch_gemm
+bool tc_gemm_supported(const GemmParams& p, int epi);
+// host: [K][ldb] fp32 -> pre-split (tf32 hi | lo), pre-swizzled shared-memory images per (n-tile, k-panel)
+size_t tc_pack_weights(const float* Bkn, int K, int N, int ldb, std::vector<float>& out);
+int launch_tc_gemm(const GemmParams& p, const float* Bimg, int epi, cudaStream_t st);
+
+}  // namespace dawn

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include "tc_gemm.cuh"
 
 namespace dawn {
 
@@ -42,7 +43,7 @@ struct Act {          // channels-last activation view: pixel stride ld, C chann
   float* p = nullptr; int ld = 0; int C = 0; int H = 0; int W = 0;
 };
 
-struct ConvW { float* w = nullptr; float* b = nullptr; int K = 0, N = 0, ldb = 0; };
+struct ConvW { float* w = nullptr; float* b = nullptr; float* img = nullptr; int K = 0, N = 0, ldb = 0; };
 
 struct CrossAttnW { float *Wkv, *nkv, *qs, *ks, *Wout, *gout; };
 
@@ -54,7 +55,7 @@ struct ResBlockW {
   float *gn1w = nullptr, *gn1b = nullptr, *gn2w = nullptr, *gn2b = nullptr;
   float *tW = nullptr, *tB = nullptr;
   float *mW[3] = {nullptr, nullptr, nullptr}, *mB[3] = {nullptr, nullptr, nullptr};   // pose, aud, eye MLPs
-  float *Wq = nullptr, *wsumq = nullptr;                                                 // [ci][192], [192]
+  float *Wq = nullptr, *wsumq = nullptr, *Wq_img = nullptr;                              // [ci][192], [192]
   CrossAttnW ca[3];
   // per-clip (depend on F / cond)
   float *film = nullptr, *kq = nullptr, *nkq = nullptr, *T = nullptr, *G = nullptr;
@@ -63,10 +64,10 @@ struct ResBlockW {
 };
 
 struct AttnW {     // temporal attention / mid spatial attention (U:648-725)
-  int C = 0; float *Wqkv = nullptr, *wsum = nullptr; ConvW out;
+  int C = 0; float *Wqkv = nullptr, *wsum = nullptr, *Wqkv_img = nullptr; ConvW out;
 };
 struct SlaW {      // spatial linear attention (U:602-627)
-  int C = 0; float *Wqkv = nullptr, *wsum = nullptr, *WoutT = nullptr, *bout = nullptr;
+  int C = 0; float *Wqkv = nullptr, *wsum = nullptr, *Wqkv_img = nullptr, *WoutT = nullptr, *bout = nullptr;
 };
 struct UpW { ConvW cls[4]; };
 
@@ -82,6 +83,7 @@ struct dawn_unet {
   int cond_dim = 0, tdim = 0;
   std::unordered_map<std::string, HostParam> raw;
   bool committed = false;
+  bool use_tc = true;                          // tcgen05 contraction path (DAWN_TC=0 falls back to mma.sync)
 
   // packed weights
   std::vector<void*> owned;                    // weight allocations
@@ -152,6 +154,15 @@ void free_all(std::vector<void*>& v) {
 }
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// tcgen05 image of a [K][ldb] weight matrix (only for shapes the tcgen05 kernel accepts)
+int upload_tc_image(dawn_unet* h, const std::vector<float>& m, int K, int N, int ldb, float** img) {
+  *img = nullptr;
+  if (!h->use_tc || N % 64 != 0 || K % 32 != 0) return 0;
+  std::vector<float> im;
+  tc_pack_weights(m.data(), K, N, ldb, im);
+  return dev_upload(h, im, img);
+}
+
 const HostParam* find(dawn_unet* h, const std::string& name) {
   auto it = h->raw.find(name);
   return it == h->raw.end() ? nullptr : &it->second;
@@ -184,6 +195,7 @@ int pack_conv(dawn_unet* h, const std::string& prefix, int co, int ci, int kh, i
       for (int t = 0; t < kh * kw; ++t)
         m[((size_t)t * ci_pad + c) * ldb + n] = w->data[((size_t)n * ci + c) * kh * kw + t];
   DAWN_TRY(dev_upload(h, m, &out->w));
+  DAWN_TRY(upload_tc_image(h, m, K, co, ldb, &out->img));
   out->b = nullptr;
   if (bias) {
     std::vector<float> bb(ldb, 0.f);
@@ -197,7 +209,7 @@ int pack_conv(dawn_unet* h, const std::string& prefix, int co, int ci, int kh, i
 // Linear weight (N, K) [+ optional per-input gain, + per-output-row scale for the first `nscale` rows]
 // -> [K][ldb], plus column sums for the LayerNorm fold
 int pack_linear(dawn_unet* h, const HostParam* w, int N, int K, const float* gain, float qscale, int nscale,
-                float** Wout, float** wsum, int* ldb_out) {
+                float** Wout, float** wsum, int* ldb_out, float** img = nullptr) {
   const int ldb = round_up(N, 64);
   std::vector<float> m((size_t)K * ldb, 0.f), s(ldb, 0.f);
   for (int n = 0; n < N; ++n) {
@@ -213,6 +225,7 @@ int pack_linear(dawn_unet* h, const HostParam* w, int N, int K, const float* gai
     s[n] = (float)acc;
   }
   DAWN_TRY(dev_upload(h, m, Wout));
+  if (img) DAWN_TRY(upload_tc_image(h, m, K, N, ldb, img));
   if (wsum) DAWN_TRY(dev_upload(h, s, wsum));
   if (ldb_out) *ldb_out = ldb;
   return 0;
@@ -269,6 +282,7 @@ int pack_resblock(dawn_unet* h, const std::string& name, int ci, int co, bool co
       DAWN_TRY(upload_raw(h, p + ".to_out.1.g", {co}, &r.ca[a].gout));
     }
     DAWN_TRY(dev_upload(h, wq, &r.Wq));
+    DAWN_TRY(upload_tc_image(h, wq, ci, 192, 192, &r.Wq_img));
     DAWN_TRY(dev_upload(h, wsum, &r.wsumq));
   }
   h->rb_index[name] = (int)h->rb.size();
@@ -283,9 +297,9 @@ int pack_attn(dawn_unet* h, const std::string& norm_name, const std::string& fn,
   DAWN_TRY(need(h, fn + ".to_out.weight", {C, 256}, &o));
   a->C = C;
   const float scale = 1.0f / sqrtf(32.0f);                                   // q * dim_head^-0.5 (U:657, 687)
-  DAWN_TRY(pack_linear(h, qkv, 768, C, g->data.data(), scale, 256, &a->Wqkv, &a->wsum, nullptr));
+  DAWN_TRY(pack_linear(h, qkv, 768, C, g->data.data(), scale, 256, &a->Wqkv, &a->wsum, nullptr, &a->Wqkv_img));
   int ldb = 0;
-  DAWN_TRY(pack_linear(h, o, C, 256, nullptr, 1.f, 0, &a->out.w, nullptr, &ldb));
+  DAWN_TRY(pack_linear(h, o, C, 256, nullptr, 1.f, 0, &a->out.w, nullptr, &ldb, &a->out.img));
   a->out.b = nullptr; a->out.K = 256; a->out.N = C; a->out.ldb = ldb;
   return 0;
 }
@@ -297,7 +311,7 @@ int pack_sla(dawn_unet* h, const std::string& p, int C, SlaW* s) {        // p =
   DAWN_TRY(need(h, p + ".fn.to_out.weight", {C, 256, 1, 1}, &o));
   DAWN_TRY(need(h, p + ".fn.to_out.bias", {C}, &b));
   s->C = C;
-  DAWN_TRY(pack_linear(h, qkv, 768, C, g->data.data(), 1.f, 0, &s->Wqkv, &s->wsum, nullptr));
+  DAWN_TRY(pack_linear(h, qkv, 768, C, g->data.data(), 1.f, 0, &s->Wqkv, &s->wsum, nullptr, &s->Wqkv_img));
   std::vector<float> wt((size_t)256 * C);
   for (int c = 0; c < C; ++c)
     for (int k = 0; k < 256; ++k) wt[(size_t)k * C + c] = o->data[(size_t)c * 256 + k];
@@ -333,6 +347,7 @@ int pack_up(dawn_unet* h, const std::string& name, int C, UpW* u) {
         }
       ConvW& cw = u->cls[py * 2 + px];
       DAWN_TRY(dev_upload(h, m, &cw.w));
+      DAWN_TRY(upload_tc_image(h, m, 4 * C, C, ldb, &cw.img));
       cw.b = bdev; cw.K = 4 * C; cw.N = C; cw.ldb = ldb;
     }
   return 0;
@@ -350,7 +365,7 @@ void base_params(GemmParams& p, const Act& in, int F) {
   p.q_post_scale = 1.f;
 }
 void set_weights(GemmParams& p, const ConvW& w) {
-  p.B = w.w; p.ldb = w.ldb; p.b_batch_stride = 0; p.N = w.N; p.K = w.K; p.bias = w.b;
+  p.B = w.w; p.Bimg = w.img; p.ldb = w.ldb; p.b_batch_stride = 0; p.N = w.N; p.K = w.K; p.bias = w.b;
 }
 void set_square_taps(GemmParams& p, int k, int pad) {
   p.ntaps = k * k;
@@ -410,6 +425,7 @@ int Ctx::gemm(const GemmParams& p, int epi, int cat) {
   if (p.Y) bytes += 4.0 * p.M * p.N;
   if (epi == EPI_CA_GATE) bytes = 4.0 * p.M * (p.Cin + 24.0);
   ProfScope ps(*this, cat, flops, bytes);
+  if (h->use_tc && p.Bimg != nullptr && tc_gemm_supported(p, epi)) return launch_tc_gemm(p, p.Bimg, epi, st);
   return launch_gemm(p, epi, st);
 }
 
@@ -438,7 +454,7 @@ int resblock(Ctx& c, const ResBlockW& r, const Act& x, const Act& out) {
       DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
     }
     GemmParams p; base_params(p, x, F);
-    p.B = r.Wq; p.ldb = 192; p.N = 192; p.K = r.ci;
+    p.B = r.Wq; p.Bimg = r.Wq_img; p.ldb = 192; p.N = 192; p.K = r.ci;
     p.rowstats = h->ROWSTATS; p.wsum = r.wsumq; p.kq = r.kq; p.nkq = r.nkq; p.gates = h->GATES;
     DAWN_TRY(c.gemm(p, EPI_CA_GATE, PC_CA_GATE));
     ProfScope ps(c, PC_CA_RSTD, 0, 4.0 * M * 56);
@@ -487,7 +503,7 @@ int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const st
   }
   {
     GemmParams p; base_params(p, x, F);
-    p.B = w.Wqkv; p.ldb = 768; p.N = 768; p.K = x.C;
+    p.B = w.Wqkv; p.Bimg = w.Wqkv_img; p.ldb = 768; p.N = 768; p.K = x.C;
     p.rowstats = h->ROWSTATS; p.wsum = w.wsum; p.rot = h->ROT;
     p.Out = h->QKV; p.ldo = 768;
     DAWN_TRY(c.gemm(p, EPI_QKV_TEMPORAL, PC_QKV));
@@ -522,7 +538,7 @@ int mid_spatial_attn(Ctx& c, const AttnW& w, const Act& x, const std::string& na
   }
   {
     GemmParams p; base_params(p, x, F);
-    p.B = w.Wqkv; p.ldb = 768; p.N = 768; p.K = x.C;
+    p.B = w.Wqkv; p.Bimg = w.Wqkv_img; p.ldb = 768; p.N = 768; p.K = x.C;
     p.rowstats = h->ROWSTATS; p.wsum = w.wsum;
     p.Out = h->QKV; p.ldo = 768;
     DAWN_TRY(c.gemm(p, EPI_QKV_MID, PC_QKV));
@@ -555,7 +571,7 @@ int sla(Ctx& c, const SlaW& w, const Act& x, const std::string& name) {
   }
   {
     GemmParams p; base_params(p, x, F);
-    p.B = w.Wqkv; p.ldb = 768; p.N = 768; p.K = x.C;
+    p.B = w.Wqkv; p.Bimg = w.Wqkv_img; p.ldb = 768; p.N = 768; p.K = x.C;
     p.rowstats = h->ROWSTATS; p.wsum = w.wsum; p.q_post_scale = 1.0f / sqrtf(32.0f);
     p.Out = h->QKV; p.ldo = 768;
     DAWN_TRY(c.gemm(p, EPI_QKV_SLA, PC_QKV));
@@ -734,6 +750,7 @@ int dawn_unet_create(const dawn_unet_cfg* cfg, dawn_unet** out) {
   DAWN_CHECK(cfg->win_width >= 1 && cfg->win_width <= 120, "win_width out of range");
   dawn_unet* h = new dawn_unet();
   h->cfg = *cfg;
+  { const char* e = getenv("DAWN_TC"); h->use_tc = !(e && e[0] == '0'); }
   h->nlev = cfg->n_levels;
   h->dims.push_back(cfg->dim);
   for (int i = 0; i < cfg->n_levels; ++i) h->dims.push_back(cfg->dim * cfg->dim_mults[i]);
@@ -1051,5 +1068,59 @@ int dawn_unet_profile_read(dawn_unet* h, double* ms, double* flops, double* byte
   return 0;
 }
 int64_t dawn_unet_workspace_bytes(dawn_unet* h) { return h ? h->ws_bytes : 0; }
+
+// random k x k conv through both contraction kernels; reports max |tcgen05 - mma.sync| over outputs and GN statistics
+int dawn_selftest_tc_gemm(int F, int H, int W, int Cin, int N, int ksize, int with_stats, float* max_abs_diff, float* max_abs_ref) {
+  DAWN_CHECK(max_abs_diff && max_abs_ref, "null argument");
+  const int M = F * H * W, K = ksize * ksize * Cin, ldb = round_up(N, 64);
+  std::vector<float> hA((size_t)M * Cin), hB((size_t)K * ldb, 0.f), hb(ldb, 0.f);
+  uint32_t seed = 12345u;
+  auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return ((seed >> 8) & 0xFFFF) / 32768.0f - 1.0f; };
+  for (auto& v : hA) v = rnd();
+  for (int k = 0; k < K; ++k) for (int n = 0; n < N; ++n) hB[(size_t)k * ldb + n] = rnd() * 0.05f;
+  for (int n = 0; n < N; ++n) hb[n] = rnd();
+  std::vector<float> img;
+  tc_pack_weights(hB.data(), K, N, ldb, img);
+  std::vector<void*> own;
+  float *dA, *dB, *db, *dImg, *dO1, *dO2, *dS;
+  auto cleanup = [&]() { free_all(own); };
+  if (dev_alloc(own, hA.size(), &dA) || dev_alloc(own, hB.size(), &dB) || dev_alloc(own, hb.size(), &db) ||
+      dev_alloc(own, img.size(), &dImg) || dev_alloc(own, (size_t)M * N, &dO1) || dev_alloc(own, (size_t)M * N, &dO2) ||
+      dev_alloc(own, 64, &dS)) { cleanup(); return -2; }
+  cudaMemcpy(dA, hA.data(), hA.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, hB.data(), hB.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(db, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dImg, img.data(), img.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemset(dS, 0, 64 * 4);
+  Act in{dA, Cin, Cin, H, W};
+  GemmParams p; base_params(p, in, F);
+  p.B = dB; p.Bimg = dImg; p.ldb = ldb; p.N = N; p.K = K; p.bias = db;
+  set_square_taps(p, ksize, ksize / 2);
+  if (with_stats) { p.stats = (double*)dS; p.cpg = N / 8; }
+  p.Out = dO1; p.ldo = N;
+  int rc = launch_gemm(p, EPI_PLAIN, 0);
+  if (rc == 0) {
+    if (with_stats) p.stats = (double*)dS + 16;
+    p.Out = dO2;
+    if (!tc_gemm_supported(p, EPI_PLAIN)) { cleanup(); set_last_error("selftest: shape not supported by tc_gemm"); return -1; }
+    rc = launch_tc_gemm(p, dImg, EPI_PLAIN, 0);
+  }
+  if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) { set_last_error(std::string("selftest: ") + cudaGetErrorString(cudaGetLastError())); rc = -2; }
+  if (rc == 0) {
+    std::vector<float> o1((size_t)M * N), o2((size_t)M * N);
+    cudaMemcpy(o1.data(), dO1, o1.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(o2.data(), dO2, o2.size() * 4, cudaMemcpyDeviceToHost);
+    float md = 0.f, mr = 0.f;
+    for (size_t i = 0; i < o1.size(); ++i) { md = std::max(md, std::fabs(o1[i] - o2[i])); mr = std::max(mr, std::fabs(o1[i])); }
+    if (with_stats) {
+      double st[32];
+      cudaMemcpy(st, dS, sizeof(st), cudaMemcpyDeviceToHost);
+      for (int i = 0; i < 16; ++i) md = std::max(md, (float)(std::fabs(st[i] - st[16 + i]) / std::max(1.0, std::fabs(st[i]))));
+    }
+    *max_abs_diff = md; *max_abs_ref = mr;
+  }
+  cleanup();
+  return rc;
+}
 
 }  // extern "C"

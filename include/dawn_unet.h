@@ -96,6 +96,10 @@ int64_t dawn_unet_last_launch_count(dawn_unet* h);
 /* bytes of device workspace currently held */
 int64_t dawn_unet_workspace_bytes(dawn_unet* h);
 
+/* self-test of the tcgen05 contraction kernel against the mma.sync kernel on a random k x k convolution
+ * (F frames of H x W, Cin -> N channels); reports max |difference| (outputs and, if requested, GroupNorm sums). */
+int dawn_selftest_tc_gemm(int F, int H, int W, int Cin, int N, int ksize, int with_stats, float* max_abs_diff, float* max_abs_ref);
+
 const char* dawn_last_error(void);
 const char* dawn_build_info(void);
 
