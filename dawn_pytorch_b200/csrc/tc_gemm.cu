@@ -8,8 +8,9 @@
 //     error (measured 1.4e-4 at K=14112).  So TMEM holds TWO accumulator buffers; every CHUNK panels the issuer
 //     flips buffers (first MMA overwrites) and the epilogue warps drain the finished buffer into fp32 registers
 //     with ordinary round-to-nearest adds while the next chunk is already being multiplied.
-//   * persistent CTAs, warp roles: 0-3 A producers (gather + split + swizzled st.shared), 4-7 accumulate/epilogue
-//     (each thread owns one output row), 8 MMA issuer (one elected thread), 9 weight loader (one elected thread).
+//   * persistent CTAs, warp roles: 0-7 A producers (gather + split + swizzled st.shared, global loads prefetched
+//     two panels ahead in registers), 8-11 accumulate/epilogue (each thread owns one output row), 12 MMA issuer
+//     (one elected thread), 13 weight loader (one elected thread).
 #include "common.cuh"
 #include "gemm.cuh"
 #include "tc_gemm.cuh"
@@ -25,7 +26,8 @@ constexpr int CHUNK = 4;                // panels accumulated inside TMEM before
 constexpr int A_PANEL = BM * 128;       // 16 KB
 constexpr int B_PANEL = BN * 128;       // 8 KB
 constexpr int STAGE_BYTES = 2 * A_PANEL + 2 * B_PANEL;     // A_hi, A_lo, B_hi, B_lo = 48 KB
-constexpr int NTHREADS = 320;
+constexpr int NPROD = 256;               // producer threads (warps 0-7)
+constexpr int NTHREADS = 448;            // + epilogue warps 8-11, MMA warp 12, loader warp 13
 constexpr int TMEM_COLS = 2 * BN;       // two accumulator buffers
 constexpr int SMEM_DYN = STAGES * STAGE_BYTES + 1024;      // + alignment slack
 
@@ -112,12 +114,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&a_full[s], 128); mbar_init(&b_full[s], 1); mbar_init(&slot_free[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&a_full[s], NPROD); mbar_init(&b_full[s], 1); mbar_init(&slot_free[s], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     mbar_init(&acc_free[0], 128); mbar_init(&acc_free[1], 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == 12) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -130,17 +132,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
   const int Ps = p.OHs * p.OWs;
   const int chunks_per_tap = p.Cin / BKP;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // =============================================================== A producers
     const int c16 = tid & 7;            // 16-byte chunk inside the 128-byte row
-    const int r0 = tid >> 3;            // rows r0 + 16 q
+    const int r0 = tid >> 3;            // rows r0 + 32 q, q = 0..3
     uint32_t it = 0;
     int tile_iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
       const int m0 = (tile / tiles_n) * BM;
       RowInfo* rows = s_rows[tile_iter & 1];
-      // row table for this tile (double-buffered across tiles; synchronised among the 128 producers only)
-      {
+      // row table for this tile (double-buffered across tiles; synchronised among the producers only)
+      if (tid < BM) {
         const int m = m0 + tid;
         RowInfo ri;
         if (m < p.M) {
@@ -152,38 +154,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
         }
         rows[tid] = ri;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int kc = 0; kc < KC; ++kc, ++it) {
-        const int s = it % STAGES;
-        const uint32_t round = it / STAGES;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+
+      auto load_panel = [&](float4 (&v)[4], int kc) {
         const int tap = kc / chunks_per_tap;
         const int c0 = (kc - tap * chunks_per_tap) * BKP;
         const int dy = p.dy[tap], dx = p.dx[tap];
-        float4 v[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const RowInfo ri = rows[r0 + 16 * q];
+        for (int q = 0; q < 4; ++q) {
+          const RowInfo ri = rows[r0 + 32 * q];
           const int iy = ri.iy + dy, ix = ri.ix + dx;
           const bool ok = (ri.pix >= 0) && (iy >= 0) && (iy < p.IH) && (ix >= 0) && (ix < p.IW);
           v[q] = ok ? __ldg(reinterpret_cast<const float4*>(p.A + (size_t)(ri.pix + iy * p.IW + ix) * p.lda + c0) + c16)
                     : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+      };
+      auto store_panel = [&](const float4 (&v)[4]) {
+        const int s = it % STAGES;
+        const uint32_t round = it / STAGES;
         mbar_wait(&slot_free[s], (round & 1) ^ 1);
         uint8_t* a_hi = smem + s * STAGE_BYTES;
         uint8_t* a_lo = a_hi + A_PANEL;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
           uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
           split_tf32(v[q].x, h0, l0); split_tf32(v[q].y, h1, l1); split_tf32(v[q].z, h2, l2); split_tf32(v[q].w, h3, l3);
-          const uint32_t off = swz(r0 + 16 * q, c16);
+          const uint32_t off = swz(r0 + 32 * q, c16);
           *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h0, h1, h2, h3);
           *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l0, l1, l2, l3);
         }
         fence_proxy_async();
         mbar_arrive(&a_full[s]);
+        ++it;
+      };
+
+      // global loads run two panels ahead of the split/store (three register buffers, statically indexed)
+      float4 v0[4], v1[4], v2[4];
+      load_panel(v0, 0);
+      if (KC > 1) load_panel(v1, 1);
+      for (int kc = 0; kc < KC; kc += 3) {
+        if (kc + 2 < KC) load_panel(v2, kc + 2);
+        store_panel(v0);
+        if (kc + 1 < KC) {
+          if (kc + 3 < KC) load_panel(v0, kc + 3);
+          store_panel(v1);
+        }
+        if (kc + 2 < KC) {
+          if (kc + 4 < KC) load_panel(v1, kc + 4);
+          store_panel(v2);
+        }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     // =============================================================== weight loader (pre-swizzled hi|lo images)
     if (lane == 0) {
       uint32_t it = 0;
@@ -199,7 +221,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
         }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // =============================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -235,11 +257,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
       }
     }
   } else {
-    // =============================================================== accumulate + epilogue (warps 4..7)
-    const int ew = warp - 4;                              // == warp % 4 -> TMEM lanes 32*ew .. 32*ew+31
+    // =============================================================== accumulate + epilogue (warps 8..11)
+    const int ew = warp - 8;                              // == warp % 4 -> TMEM lanes 32*ew .. 32*ew+31
     const int row_in_tile = ew * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
-    const int etid = tid - 128;
+    const int etid = tid - NPROD;
     uint32_t cg = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
@@ -377,7 +399,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 8) {
+  if (warp == 12) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
 }
