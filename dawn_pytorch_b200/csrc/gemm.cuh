@@ -48,6 +48,7 @@ struct GemmParams {
   const float* Y; int ldy; const double* gn_stats; const float* gn_w; const float* gn_b;
   const float* film;       // [2N] scale | shift, or null
   double gn_count;         // elements per group
+  unsigned long long* trace;   // optional [16] cycle counters written by CTA 0 of the tcgen05 kernel (debug)
 };
 
 int launch_gemm(const GemmParams& p, int epi, cudaStream_t st);

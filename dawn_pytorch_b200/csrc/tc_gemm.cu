@@ -172,7 +172,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
       auto store_panel = [&](const float4 (&v)[4]) {
         const int s = it % STAGES;
         const uint32_t round = it / STAGES;
+        const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && tid == 0;
+        long long t0 = 0;
+        if (tr) t0 = clock64();
         mbar_wait(&slot_free[s], (round & 1) ^ 1);
+        if (tr) { const long long t1 = clock64(); p.trace[6] += (unsigned long long)(t1 - t0); t0 = t1; }
         uint8_t* a_hi = smem + s * STAGE_BYTES;
         uint8_t* a_lo = a_hi + A_PANEL;
 #pragma unroll
@@ -185,6 +189,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
         }
         fence_proxy_async();
         mbar_arrive(&a_full[s]);
+        if (tr) p.trace[7] += (unsigned long long)(clock64() - t0);
         ++it;
       };
 
@@ -215,7 +220,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
         for (int kc = 0; kc < KC; ++kc, ++it) {
           const int s = it % STAGES;
           const uint32_t round = it / STAGES;
+          const bool tr = (p.trace != nullptr) && blockIdx.x == 0;
+          long long t0 = 0;
+          if (tr) t0 = clock64();
           mbar_wait(&slot_free[s], (round & 1) ^ 1);
+          if (tr) p.trace[8] += (unsigned long long)(clock64() - t0);
           mbar_arrive_expect_tx(&b_full[s], 2 * B_PANEL);
           bulk_copy_g2s(smem + s * STAGE_BYTES + 2 * A_PANEL, src + (size_t)kc * (2 * B_PANEL), 2 * B_PANEL, &b_full[s]);
         }
@@ -226,6 +235,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       uint32_t it = 0, cg = 0;
+      const bool tr = (p.trace != nullptr) && blockIdx.x == 0;
+      long long t_acc = 0, t_a = 0, t_b = 0, t_issue = 0, t0 = 0, t_begin = clock64();
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         for (int kc = 0; kc < KC; ++kc, ++it) {
           const int s = it % STAGES;
@@ -233,12 +244,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
           const bool chunk_first = (kc % CHUNK) == 0;
           const bool chunk_last = ((kc % CHUNK) == CHUNK - 1) || (kc == KC - 1);
           const uint32_t buf = cg & 1;
+          if (tr) t0 = clock64();
           if (chunk_first) {
             mbar_wait(&acc_free[buf], ((cg >> 1) & 1) ^ 1);
             tc_fence_after();
           }
+          if (tr) { const long long t1 = clock64(); t_acc += t1 - t0; t0 = t1; }
           mbar_wait(&a_full[s], round & 1);
+          if (tr) { const long long t1 = clock64(); t_a += t1 - t0; t0 = t1; }
           mbar_wait(&b_full[s], round & 1);
+          if (tr) { const long long t1 = clock64(); t_b += t1 - t0; t0 = t1; }
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint64_t ahi = make_desc(sa), alo = make_desc(sa + A_PANEL);
@@ -253,7 +268,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
           }
           tc_commit(&slot_free[s]);
           if (chunk_last) { tc_commit(&acc_full[buf]); ++cg; }
+          if (tr) t_issue += clock64() - t0;
         }
+      }
+      if (tr) {
+        p.trace[0] = (unsigned long long)(clock64() - t_begin); p.trace[1] = it;
+        p.trace[2] = (unsigned long long)t_acc; p.trace[3] = (unsigned long long)t_a;
+        p.trace[4] = (unsigned long long)t_b; p.trace[5] = (unsigned long long)t_issue;
       }
     }
   } else {
@@ -271,7 +292,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
       const int nchunks = (KC + CHUNK - 1) / CHUNK;
       for (int c = 0; c < nchunks; ++c, ++cg) {
         const uint32_t buf = cg & 1;
+        const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && etid == 0;
+        long long t0 = 0;
+        if (tr) t0 = clock64();
         mbar_wait(&acc_full[buf], (cg >> 1) & 1);
+        if (tr) p.trace[9] += (unsigned long long)(clock64() - t0);
         tc_fence_after();
 #pragma unroll
         for (int hlf = 0; hlf < BN / 32; ++hlf) {
@@ -285,6 +310,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
       }
 
       // ---------------------------------------------------------- final epilogue: this thread owns row m
+      const bool tr_e = (p.trace != nullptr) && blockIdx.x == 0 && etid == 0;
+      const long long te0 = tr_e ? clock64() : 0;
       const int m = m0 + row_in_tile;
       const bool rv = m < p.M;
       const int mc = rv ? m : (p.M - 1);
@@ -393,6 +420,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
           for (int i = 0; i < BN / 4; ++i) op[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
         }
       }
+      if (tr_e) p.trace[10] += (unsigned long long)(clock64() - te0);
     }
   }
 

@@ -12,6 +12,9 @@ CASES = [  # F, H, W, Cin, N, k, stats
     (2, 16, 16, 256, 512, 1, 0),
     (16, 8, 8, 1024, 256, 3, 1),
     (40, 64, 64, 64, 64, 3, 1),     # 1280 tiles: persistent loop over many tiles per CTA
+    (100, 64, 64, 64, 64, 3, 1),
+    (100, 32, 32, 128, 128, 3, 1),
+    (100, 64, 64, 64, 768, 1, 0),
 ]
 
 
