@@ -54,11 +54,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// 3xTF32 split: x ~= hi + lo with hi, lo representable in tf32 (10-bit mantissa), round-to-nearest.
+// 3xTF32 split: x ~= hi + lo with hi, lo representable in tf32 (10-bit mantissa), round-to-nearest (ties away),
+// done with full-rate integer ops: cvt.rna.tf32.f32 issues on a slow conversion pipe and was the measured
+// bottleneck of both contraction kernels' operand preparation.
+__device__ __forceinline__ uint32_t tf32_rn_bits(uint32_t u) { return (u + 0x1000u) & 0xFFFFE000u; }
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = tf32_rn_bits(__float_as_uint(x));
+  lo = tf32_rn_bits(__float_as_uint(x - __uint_as_float(hi)));
 }
 
 // D(16x8, f32) += A(16x8, tf32, row) * B(8x8, tf32, col)

@@ -19,17 +19,24 @@ namespace dawn {
 namespace {
 
 constexpr int BM = 128;
-constexpr int BN = 64;
 constexpr int BKP = 32;                 // floats per panel row (128 bytes)
-constexpr int STAGES = 4;
 constexpr int CHUNK = 4;                // panels accumulated inside TMEM before a drain (K = 128)
 constexpr int A_PANEL = BM * 128;       // 16 KB
-constexpr int B_PANEL = BN * 128;       // 8 KB
-constexpr int STAGE_BYTES = 2 * A_PANEL + 2 * B_PANEL;     // A_hi, A_lo, B_hi, B_lo = 48 KB
-constexpr int NPROD = 256;               // producer threads (warps 0-7)
-constexpr int NTHREADS = 448;            // + epilogue warps 8-11, MMA warp 12, loader warp 13
-constexpr int TMEM_COLS = 2 * BN;       // two accumulator buffers
-constexpr int SMEM_DYN = STAGES * STAGE_BYTES + 1024;      // + alignment slack
+constexpr int NPROD = 256;              // producer threads (warps 0-7)
+
+// BN = 64: one epilogue warpgroup, 4 stages of 48 KB.  BN = 128: two epilogue warpgroups (64 columns each), 3 stages of 64 KB.
+template <int BN>
+struct Cfg {
+  static constexpr int NWG = BN / 64;                        // epilogue warpgroups
+  static constexpr int B_PANEL = BN * 128;
+  static constexpr int STAGE_BYTES = 2 * A_PANEL + 2 * B_PANEL;
+  static constexpr int STAGES = (BN == 64) ? 4 : 3;
+  static constexpr int NTHREADS = NPROD + 128 * NWG + 64;    // producers | epilogue | MMA warp | loader warp
+  static constexpr int MMA_WARP = (NPROD + 128 * NWG) / 32;
+  static constexpr int LOAD_WARP = MMA_WARP + 1;
+  static constexpr int TMEM_COLS = 2 * BN;                   // two accumulator buffers
+  static constexpr int SMEM_DYN = STAGES * STAGE_BYTES + 1024;
+};
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -92,6 +99,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // K-major, 128-byte-swizzled operand panel: rows of 128 B, 8-row atoms of 1024 B (SBO), descriptor version 1 (sm_100)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -101,14 +122,17 @@ __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)((r >> 
 
 struct RowInfo { int pix; short iy, ix; };     // per tile row: input frame base pixel, top-left input coordinate
 
-template <int EPI>
-__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p, const float* __restrict__ Bimg, int KC,
-                                                              int tiles_m, int tiles_n) {
+template <int EPI, int BN>
+__global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const GemmParams p, const float* __restrict__ Bimg, int KC,
+                                                                       int tiles_m, int tiles_n) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_PANEL = C::B_PANEL, TMEM_COLS = C::TMEM_COLS;
+  constexpr int MMA_WARP = C::MMA_WARP, LOAD_WARP = C::LOAD_WARP, NWG = C::NWG;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t a_full[STAGES], b_full[STAGES], slot_free[STAGES], acc_full[2], acc_free[2];
   __shared__ uint32_t s_tmem_base;
   __shared__ RowInfo s_rows[2][BM];
-  __shared__ float s_stat[16];
+  __shared__ float s_stat[NWG][16];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -116,10 +140,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&a_full[s], NPROD); mbar_init(&b_full[s], 1); mbar_init(&slot_free[s], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
-    mbar_init(&acc_free[0], 128); mbar_init(&acc_free[1], 128);
+    mbar_init(&acc_free[0], 128 * NWG); mbar_init(&acc_free[1], 128 * NWG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 12) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -210,7 +234,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
         }
       }
     }
-  } else if (warp == 13) {
+  } else if (warp == LOAD_WARP) {
     // =============================================================== weight loader (pre-swizzled hi|lo images)
     if (lane == 0) {
       uint32_t it = 0;
@@ -230,7 +254,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
         }
       }
     }
-  } else if (warp == 12) {
+  } else if (warp == MMA_WARP) {
     // =============================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -278,17 +302,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
       }
     }
   } else {
-    // =============================================================== accumulate + epilogue (warps 8..11)
-    const int ew = warp - 8;                              // == warp % 4 -> TMEM lanes 32*ew .. 32*ew+31
+    // =============================================================== accumulate + epilogue (warps 8 .. 8+4*NWG-1)
+    // warpgroup wg owns output columns [64 wg, 64 wg + 64) of the tile; inside it warp ew = warp % 4 reads TMEM lanes 32 ew ..
+    const int wg = (warp - 8) >> 2;
+    const int ew = (warp - 8) & 3;
     const int row_in_tile = ew * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
-    const int etid = tid - NPROD;
+    const int etid = (tid - NPROD) & 127;
+    float* s_st = s_stat[wg];
+    const int bar_id = 2 + wg;
+    constexpr int EN = 64;                                 // columns per epilogue thread
     uint32_t cg = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
-      float acc[BN];
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN + wg * EN;
+      float acc[EN];
 #pragma unroll
-      for (int i = 0; i < BN; ++i) acc[i] = 0.f;
+      for (int i = 0; i < EN; ++i) acc[i] = 0.f;
       const int nchunks = (KC + CHUNK - 1) / CHUNK;
       for (int c = 0; c < nchunks; ++c, ++cg) {
         const uint32_t buf = cg & 1;
@@ -299,11 +328,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
         if (tr) p.trace[9] += (unsigned long long)(clock64() - t0);
         tc_fence_after();
 #pragma unroll
-        for (int hlf = 0; hlf < BN / 32; ++hlf) {
-          float v[32];
-          tmem_ld32(tmem_base + lane_addr + buf * BN + hlf * 32, v);
+        for (int q = 0; q < EN / 16; ++q) {
+          float v[16];
+          tmem_ld16(tmem_base + lane_addr + buf * BN + wg * EN + q * 16, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[hlf * 32 + i] += v[i];
+          for (int i = 0; i < 16; ++i) acc[q * 16 + i] += v[i];
         }
         tc_fence_before();
         mbar_arrive(&acc_free[buf]);
@@ -322,12 +351,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
       if (EPI == EPI_PLAIN) {
         if (p.bias) {
 #pragma unroll
-          for (int i = 0; i < BN; ++i) acc[i] += p.bias[n0 + i];
+          for (int i = 0; i < EN; ++i) acc[i] += p.bias[n0 + i];
         }
         if (rv && p.Res) {
           const float4* rp = reinterpret_cast<const float4*>(p.Res + opix * p.ldr + n0);
 #pragma unroll
-          for (int i = 0; i < BN / 4; ++i) {
+          for (int i = 0; i < EN / 4; ++i) {
             const float4 r = rp[i];
             acc[4 * i] += r.x; acc[4 * i + 1] += r.y; acc[4 * i + 2] += r.z; acc[4 * i + 3] += r.w;
           }
@@ -335,14 +364,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
         if (rv) {
           float4* op = reinterpret_cast<float4*>(p.Out + opix * p.ldo + n0);
 #pragma unroll
-          for (int i = 0; i < BN / 4; ++i) op[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+          for (int i = 0; i < EN / 4; ++i) op[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
         }
         if (p.stats != nullptr) {
           // GroupNorm partial statistics (U:230): per 8-column sub-block, reduced over the warp's 32 rows
-          if (etid < 16) s_stat[etid] = 0.f;
-          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (etid < 16) s_st[etid] = 0.f;
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 #pragma unroll
-          for (int b8 = 0; b8 < BN / 8; ++b8) {
+          for (int b8 = 0; b8 < EN / 8; ++b8) {
             float s = 0.f, ss = 0.f;
             if (rv) {
 #pragma unroll
@@ -351,27 +380,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
             s = warp_sum(s); ss = warp_sum(ss);
             if (lane == 0) {
               const int grp = (n0 + b8 * 8) / p.cpg;
-              atomicAdd(&s_stat[2 * grp], s);
-              atomicAdd(&s_stat[2 * grp + 1], ss);
+              atomicAdd(&s_st[2 * grp], s);
+              atomicAdd(&s_st[2 * grp + 1], ss);
             }
           }
-          asm volatile("bar.sync 2, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           if (etid < 16) {
             const int grp = etid >> 1;
-            const int glo = n0 / p.cpg, ghi = (n0 + BN - 1) / p.cpg;
-            if (grp >= glo && grp <= ghi) atomicAdd(&p.stats[etid], (double)s_stat[etid]);
+            const int glo = n0 / p.cpg, ghi = (n0 + EN - 1) / p.cpg;
+            if (grp >= glo && grp <= ghi) atomicAdd(&p.stats[etid], (double)s_st[etid]);
           }
         }
       } else {
         // LayerNorm fold (see gemm.cu): v = rstd * (acc - mu * colsum)
         const float mu = p.rowstats[2 * (size_t)mc], rs = p.rowstats[2 * (size_t)mc + 1];
 #pragma unroll
-        for (int i = 0; i < BN; ++i) acc[i] = rs * (acc[i] - mu * p.wsum[n0 + i]);
+        for (int i = 0; i < EN; ++i) acc[i] = rs * (acc[i] - mu * p.wsum[n0 + i]);
         if (EPI == EPI_QKV_TEMPORAL) {
           if (n0 < 512) {
             const int fr = mc / p.P;
 #pragma unroll
-            for (int i = 0; i < BN; i += 2) {
+            for (int i = 0; i < EN; i += 2) {
               const int pi = ((n0 + i) & 31) >> 1;
               const float2 cs = *reinterpret_cast<const float2*>(p.rot + (size_t)(fr * 16 + pi) * 2);
               const float x0 = acc[i], x1 = acc[i + 1];
@@ -382,7 +411,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
         } else if (EPI == EPI_QKV_SLA) {
           if (n0 < 256) {
 #pragma unroll
-            for (int hd = 0; hd < BN / 32; ++hd) {
+            for (int hd = 0; hd < EN / 32; ++hd) {
               float mx = acc[hd * 32];
 #pragma unroll
               for (int i = 1; i < 32; ++i) mx = fmaxf(mx, acc[hd * 32 + i]);
@@ -417,7 +446,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
         } else if (rv) {
           float4* op = reinterpret_cast<float4*>(p.Out + opix * p.ldo + n0);
 #pragma unroll
-          for (int i = 0; i < BN / 4; ++i) op[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+          for (int i = 0; i < EN / 4; ++i) op[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
         }
       }
       if (tr_e) p.trace[10] += (unsigned long long)(clock64() - te0);
@@ -427,17 +456,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const GemmParams p
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 12) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
 }
 
-template <int EPI>
+template <int EPI, int BN>
 int launch_t(const GemmParams& p, const float* Bimg, cudaStream_t st) {
+  using C = Cfg<BN>;
   static bool attr_set = false;
   static int num_sms = 0;
   if (!attr_set) {
-    DAWN_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
+    DAWN_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_DYN));
     int dev = 0;
     DAWN_CUDA_OK(cudaGetDevice(&dev));
     DAWN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -446,9 +476,14 @@ int launch_t(const GemmParams& p, const float* Bimg, cudaStream_t st) {
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = p.N / BN;
   const int KC = p.K / BKP;
   const int grid = std::min(tiles_m * tiles_n, num_sms);
-  tc_gemm_kernel<EPI><<<grid, NTHREADS, SMEM_DYN, st>>>(p, Bimg, KC, tiles_m, tiles_n);
+  tc_gemm_kernel<EPI, BN><<<grid, C::NTHREADS, C::SMEM_DYN, st>>>(p, Bimg, KC, tiles_m, tiles_n);
   DAWN_LAUNCH_OK();
   return 0;
+}
+
+template <int EPI>
+int launch_bn(const GemmParams& p, const float* Bimg, cudaStream_t st) {
+  return tc_tile_n(p.N) == 128 ? launch_t<EPI, 128>(p, Bimg, st) : launch_t<EPI, 64>(p, Bimg, st);
 }
 
 inline uint32_t tf32_rna(float x) {       // cvt.rna.tf32.f32 on the host: nearest, ties away from zero
@@ -459,24 +494,28 @@ inline uint32_t tf32_rna(float x) {       // cvt.rna.tf32.f32 on the host: neare
 
 }  // namespace
 
+// output-tile width used for a problem with N columns (also decides the weight image layout)
+int tc_tile_n(int N) { return (N % 128 == 0) ? 128 : 64; }
+
 bool tc_gemm_supported(const GemmParams& p, int epi) {
   if (epi == EPI_GN_APPLY) return false;
   if (p.b_batch_stride != 0 || p.rows_per_batch != p.M) return false;
-  if (p.N % BN != 0 || p.K % BKP != 0 || p.Cin % BKP != 0) return false;
+  if (p.N % 64 != 0 || p.K % BKP != 0 || p.Cin % BKP != 0) return false;
   if ((p.lda & 3) || (p.ldo & 3) || (p.Res && (p.ldr & 3))) return false;
   if (p.M < BM) return false;
   if (epi == EPI_PLAIN && p.stats && (p.cpg % 8 != 0)) return false;
   return true;
 }
 
-// Host: [K][ldb] fp32 weights -> per (n-tile, k-panel) shared-memory images: hi panel (64 x 128 B, swizzled) | lo panel
+// Host: [K][ldb] fp32 weights -> per (n-tile, k-panel) shared-memory images: hi panel (BN x 128 B, swizzled) | lo panel
 size_t tc_pack_weights(const float* Bkn, int K, int N, int ldb, std::vector<float>& out) {
-  const int KC = K / BKP, NT = N / BN;
-  out.assign((size_t)NT * KC * 2 * (B_PANEL / 4), 0.f);
+  const int BN = tc_tile_n(N);
+  const int KC = K / BKP, NT = N / BN, PW = BN * 32;          // panel size in 4-byte words
+  out.assign((size_t)NT * KC * 2 * PW, 0.f);
   for (int nt = 0; nt < NT; ++nt)
     for (int kc = 0; kc < KC; ++kc) {
-      uint32_t* hi = reinterpret_cast<uint32_t*>(out.data()) + ((size_t)nt * KC + kc) * 2 * (B_PANEL / 4);
-      uint32_t* lo = hi + B_PANEL / 4;
+      uint32_t* hi = reinterpret_cast<uint32_t*>(out.data()) + ((size_t)nt * KC + kc) * 2 * PW;
+      uint32_t* lo = hi + PW;
       for (int n = 0; n < BN; ++n)
         for (int k = 0; k < BKP; ++k) {
           const float w = Bkn[(size_t)(kc * BKP + k) * ldb + nt * BN + n];
@@ -493,11 +532,11 @@ size_t tc_pack_weights(const float* Bkn, int K, int N, int ldb, std::vector<floa
 int launch_tc_gemm(const GemmParams& p, const float* Bimg, int epi, cudaStream_t st) {
   if (!tc_gemm_supported(p, epi)) { set_last_error("launch_tc_gemm: unsupported geometry"); return -1; }
   switch (epi) {
-    case EPI_PLAIN: return launch_t<EPI_PLAIN>(p, Bimg, st);
-    case EPI_QKV_TEMPORAL: return launch_t<EPI_QKV_TEMPORAL>(p, Bimg, st);
-    case EPI_QKV_SLA: return launch_t<EPI_QKV_SLA>(p, Bimg, st);
-    case EPI_QKV_MID: return launch_t<EPI_QKV_MID>(p, Bimg, st);
-    case EPI_CA_GATE: return launch_t<EPI_CA_GATE>(p, Bimg, st);
+    case EPI_PLAIN: return launch_bn<EPI_PLAIN>(p, Bimg, st);
+    case EPI_QKV_TEMPORAL: return launch_bn<EPI_QKV_TEMPORAL>(p, Bimg, st);
+    case EPI_QKV_SLA: return launch_bn<EPI_QKV_SLA>(p, Bimg, st);
+    case EPI_QKV_MID: return launch_bn<EPI_QKV_MID>(p, Bimg, st);
+    case EPI_CA_GATE: return launch_bn<EPI_CA_GATE>(p, Bimg, st);
   }
   set_last_error("launch_tc_gemm: bad epilogue id");
   return -1;

@@ -7,6 +7,7 @@
 namespace dawn {
 
 // true when launch_tc_gemm can run this problem (regular shapes, static weights); otherwise use launch_gemm
+int tc_tile_n(int N);
 bool tc_gemm_supported(const GemmParams& p, int epi);
 // host: [K][ldb] fp32 -> pre-split (tf32 hi | lo), pre-swizzled shared-memory images per (n-tile, k-panel)
 size_t tc_pack_weights(const float* Bkn, int K, int N, int ldb, std::vector<float>& out);
