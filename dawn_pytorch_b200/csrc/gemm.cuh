@@ -29,6 +29,7 @@ struct GemmParams {
   // B operand [K][ldb] (ldb multiple of 64, zero padded)
   const float* B; int ldb; long long b_batch_stride;
   const float* Bimg;       // optional tcgen05 image of B (tc_pack_weights), or null
+  float tc_scale;          // accumulator rescale of the tcgen05 path: 1 / (activation scale * weight image scale)
   // output
   float* Out; int ldo; int OH, OW, out_stride, oy0, ox0;
   const float* bias;

@@ -1,9 +1,13 @@
 // tcgen05 implicit GEMM for the DAWN UNet contractions (sm_100a): Out = epilogue(A (gathered, fp32) x B (weights)).
 //
-//   * 128-row position tile x 64-column output tile, K streamed in 32-float panels (= one 128-byte swizzle row).
-//   * fp32-level parity needs the 3-term split  hi*hi + hi*lo + lo*hi   -> kind::tf32 MMAs on
-//     (A_lo,B_hi), (A_hi,B_lo), (A_hi,B_hi); A is split on the fly by the producer warps, B is pre-split and
-//     pre-swizzled on the host into ready-to-copy shared-memory images (1-D bulk copies, no tensor maps).
+//   * 128-row position tile x 64/128-column output tile, K streamed in 64-element panels (= one 128-byte swizzle row of fp16).
+//   * fp32-level parity needs the 3-term split  hi*hi + hi*lo + lo*hi  (SURVEY App. D).  The pieces are FP16
+//     (kind::f16, K = 16 per instruction): an fp16 piece carries the same 11-bit significand as a TF32 piece, so
+//     hi+lo keeps ~22 bits like 3xTF32, but every tcgen05.mma does twice the work and reads half the bytes
+//     (measured: ~70 cycles of issue cost per tcgen05.mma regardless of N made the K=8 TF32 form issue-bound).
+//     fp16's narrow exponent is handled with exact power-of-two pre-scales (activations x8, weights x2^k per matrix)
+//     undone in the epilogue.  A is split on the fly by the producer warps, B is pre-split and pre-swizzled on the
+//     host into ready-to-copy shared-memory images (1-D bulk copies, no tensor maps).
 //   * The tensor core adds into its accumulator with round-toward-zero; chained over a long K that is a biased
 //     error (measured 1.4e-4 at K=14112).  So TMEM holds TWO accumulator buffers; every CHUNK panels the issuer
 //     flips buffers (first MMA overwrites) and the epilogue warps drain the finished buffer into fp32 registers
@@ -11,6 +15,7 @@
 //   * persistent CTAs, warp roles: 0-7 A producers (gather + split + swizzled st.shared, global loads prefetched
 //     two panels ahead in registers), 8-11 accumulate/epilogue (each thread owns one output row), 12 MMA issuer
 //     (one elected thread), 13 weight loader (one elected thread).
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "gemm.cuh"
 #include "tc_gemm.cuh"
@@ -19,7 +24,8 @@ namespace dawn {
 namespace {
 
 constexpr int BM = 128;
-constexpr int BKP = 32;                 // floats per panel row (128 bytes)
+constexpr int BKP = 64;                 // K elements per panel row (64 fp16 = 128 bytes)
+constexpr float A_SCALE = 8.0f;         // exact pre-scale of activations before the fp16 split
 constexpr int CHUNK = 4;                // panels accumulated inside TMEM before a drain (K = 128)
 constexpr int A_PANEL = BM * 128;       // 16 KB
 constexpr int NPROD = 256;              // producer threads (warps 0-7)
@@ -73,12 +79,12 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -119,6 +125,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 }
 // byte offset of 16-byte chunk c (0..7) of row r inside a swizzled panel
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
+
+// (x0, x1) * A_SCALE -> packed fp16 hi pair and fp16 lo pair (lo = residual of the hi rounding)
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  x0 *= A_SCALE; x1 *= A_SCALE;
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 struct RowInfo { int pix; short iy, ix; };     // per tile row: input frame base pixel, top-left input coordinate
 
@@ -180,7 +196,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
 
-      auto load_panel = [&](float4 (&v)[4], int kc) {
+      auto load_panel = [&](float4 (&v)[8], int kc) {
         const int tap = kc / chunks_per_tap;
         const int c0 = (kc - tap * chunks_per_tap) * BKP;
         const int dy = p.dy[tap], dx = p.dx[tap];
@@ -189,11 +205,17 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
           const RowInfo ri = rows[r0 + 32 * q];
           const int iy = ri.iy + dy, ix = ri.ix + dx;
           const bool ok = (ri.pix >= 0) && (iy >= 0) && (iy < p.IH) && (ix >= 0) && (ix < p.IW);
-          v[q] = ok ? __ldg(reinterpret_cast<const float4*>(p.A + (size_t)(ri.pix + iy * p.IW + ix) * p.lda + c0) + c16)
-                    : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) {
+            const float4* src = reinterpret_cast<const float4*>(p.A + (size_t)(ri.pix + iy * p.IW + ix) * p.lda + c0) + 2 * c16;
+            v[2 * q] = __ldg(src);
+            v[2 * q + 1] = __ldg(src + 1);
+          } else {
+            v[2 * q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            v[2 * q + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
       };
-      auto store_panel = [&](const float4 (&v)[4]) {
+      auto store_panel = [&](const float4 (&v)[8]) {
         const int s = it % STAGES;
         const uint32_t round = it / STAGES;
         const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && tid == 0;
@@ -205,11 +227,14 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
         uint8_t* a_lo = a_hi + A_PANEL;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-          split_tf32(v[q].x, h0, l0); split_tf32(v[q].y, h1, l1); split_tf32(v[q].z, h2, l2); split_tf32(v[q].w, h3, l3);
+          uint32_t h[4], l[4];
+          split_f16x2(v[2 * q].x, v[2 * q].y, h[0], l[0]);
+          split_f16x2(v[2 * q].z, v[2 * q].w, h[1], l[1]);
+          split_f16x2(v[2 * q + 1].x, v[2 * q + 1].y, h[2], l[2]);
+          split_f16x2(v[2 * q + 1].z, v[2 * q + 1].w, h[3], l[3]);
           const uint32_t off = swz(r0 + 32 * q, c16);
-          *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h0, h1, h2, h3);
-          *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l0, l1, l2, l3);
+          *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
         }
         fence_proxy_async();
         mbar_arrive(&a_full[s]);
@@ -217,20 +242,34 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
         ++it;
       };
 
-      // global loads run two panels ahead of the split/store (three register buffers, statically indexed)
-      float4 v0[4], v1[4], v2[4];
-      load_panel(v0, 0);
-      if (KC > 1) load_panel(v1, 1);
-      for (int kc = 0; kc < KC; kc += 3) {
-        if (kc + 2 < KC) load_panel(v2, kc + 2);
-        store_panel(v0);
-        if (kc + 1 < KC) {
-          if (kc + 3 < KC) load_panel(v0, kc + 3);
-          store_panel(v1);
+      // global loads run ahead of the split/store in statically indexed register buffers:
+      // two panels ahead (3 buffers) for BN = 64, one panel ahead (2 buffers) for BN = 128 (96-register budget)
+      if constexpr (BN == 64) {
+        float4 v0[8], v1[8], v2[8];
+        load_panel(v0, 0);
+        if (KC > 1) load_panel(v1, 1);
+        for (int kc = 0; kc < KC; kc += 3) {
+          if (kc + 2 < KC) load_panel(v2, kc + 2);
+          store_panel(v0);
+          if (kc + 1 < KC) {
+            if (kc + 3 < KC) load_panel(v0, kc + 3);
+            store_panel(v1);
+          }
+          if (kc + 2 < KC) {
+            if (kc + 4 < KC) load_panel(v1, kc + 4);
+            store_panel(v2);
+          }
         }
-        if (kc + 2 < KC) {
-          if (kc + 4 < KC) load_panel(v1, kc + 4);
-          store_panel(v2);
+      } else {
+        float4 v0[8], v1[8];
+        load_panel(v0, 0);
+        for (int kc = 0; kc < KC; kc += 2) {
+          if (kc + 1 < KC) load_panel(v1, kc + 1);
+          store_panel(v0);
+          if (kc + 1 < KC) {
+            if (kc + 2 < KC) load_panel(v0, kc + 2);
+            store_panel(v1);
+          }
         }
       }
     }
@@ -257,7 +296,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
   } else if (warp == MMA_WARP) {
     // =============================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // D f32, A/B f16, K-major
       uint32_t it = 0, cg = 0;
       const bool tr = (p.trace != nullptr) && blockIdx.x == 0;
       long long t_acc = 0, t_a = 0, t_b = 0, t_issue = 0, t0 = 0, t_begin = clock64();
@@ -284,11 +323,11 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
           const uint64_t bhi = make_desc(sa + 2 * A_PANEL), blo = make_desc(sa + 2 * A_PANEL + B_PANEL);
           const uint32_t d = tmem_base + buf * BN;
 #pragma unroll
-          for (int j = 0; j < BKP / 8; ++j) {
+          for (int j = 0; j < BKP / 16; ++j) {
             const uint64_t o = (uint64_t)(j * 2);               // +32 bytes per k-step, in 16-byte units
-            tc_mma_tf32(d, alo + o, bhi + o, idesc, (chunk_first && j == 0) ? 0u : 1u);
-            tc_mma_tf32(d, ahi + o, blo + o, idesc, 1u);
-            tc_mma_tf32(d, ahi + o, bhi + o, idesc, 1u);
+            tc_mma_f16(d, alo + o, bhi + o, idesc, (chunk_first && j == 0) ? 0u : 1u);
+            tc_mma_f16(d, ahi + o, blo + o, idesc, 1u);
+            tc_mma_f16(d, ahi + o, bhi + o, idesc, 1u);
           }
           tc_commit(&slot_free[s]);
           if (chunk_last) { tc_commit(&acc_full[buf]); ++cg; }
@@ -337,6 +376,9 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
         tc_fence_before();
         mbar_arrive(&acc_free[buf]);
       }
+
+#pragma unroll
+      for (int i = 0; i < EN; ++i) acc[i] *= p.tc_scale;       // undo the exact power-of-two operand pre-scales
 
       // ---------------------------------------------------------- final epilogue: this thread owns row m
       const bool tr_e = (p.trace != nullptr) && blockIdx.x == 0 && etid == 0;
@@ -486,12 +528,6 @@ int launch_bn(const GemmParams& p, const float* Bimg, cudaStream_t st) {
   return tc_tile_n(p.N) == 128 ? launch_t<EPI, 128>(p, Bimg, st) : launch_t<EPI, 64>(p, Bimg, st);
 }
 
-inline uint32_t tf32_rna(float x) {       // cvt.rna.tf32.f32 on the host: nearest, ties away from zero
-  uint32_t u; memcpy(&u, &x, 4);
-  u = (u + 0x1000u) & 0xFFFFE000u;
-  return u;
-}
-
 }  // namespace
 
 // output-tile width used for a problem with N columns (also decides the weight image layout)
@@ -500,29 +536,38 @@ int tc_tile_n(int N) { return (N % 128 == 0) ? 128 : 64; }
 bool tc_gemm_supported(const GemmParams& p, int epi) {
   if (epi == EPI_GN_APPLY) return false;
   if (p.b_batch_stride != 0 || p.rows_per_batch != p.M) return false;
-  if (p.N % 64 != 0 || p.K % BKP != 0 || p.Cin % BKP != 0) return false;
+  if (p.N % 64 != 0 || p.K % BKP != 0 || p.Cin % BKP != 0) return false;      // 64-channel panels
   if ((p.lda & 3) || (p.ldo & 3) || (p.Res && (p.ldr & 3))) return false;
   if (p.M < BM) return false;
   if (epi == EPI_PLAIN && p.stats && (p.cpg % 8 != 0)) return false;
   return true;
 }
 
-// Host: [K][ldb] fp32 weights -> per (n-tile, k-panel) shared-memory images: hi panel (BN x 128 B, swizzled) | lo panel
-size_t tc_pack_weights(const float* Bkn, int K, int N, int ldb, std::vector<float>& out) {
+// Host: [K][ldb] fp32 weights -> per (n-tile, k-panel) shared-memory images: hi panel (BN rows x 64 fp16, 128-byte
+// swizzled) | lo panel.  Weights are multiplied by the exact power of two `*scale` first so that the lo pieces
+// stay fp16-normal; returns the image size in floats.
+size_t tc_pack_weights(const float* Bkn, int K, int N, int ldb, std::vector<float>& out, float* scale) {
   const int BN = tc_tile_n(N);
-  const int KC = K / BKP, NT = N / BN, PW = BN * 32;          // panel size in 4-byte words
-  out.assign((size_t)NT * KC * 2 * PW, 0.f);
+  const int KC = K / BKP, NT = N / BN, PH = BN * 64;           // panel size in fp16 elements
+  float mx = 0.f;
+  for (int k = 0; k < K; ++k)
+    for (int n = 0; n < N; ++n) mx = std::max(mx, std::fabs(Bkn[(size_t)k * ldb + n]));
+  int e = 0;
+  if (mx > 0.f) { std::frexp(mx, &e); }                        // mx = m * 2^e, m in [0.5, 1)
+  const float sc = std::ldexp(1.0f, 11 - e);                   // max |w| * sc in [1024, 2048)
+  *scale = sc;
+  out.assign(((size_t)NT * KC * 2 * PH + 1) / 2, 0.f);
+  __half* base = reinterpret_cast<__half*>(out.data());
   for (int nt = 0; nt < NT; ++nt)
     for (int kc = 0; kc < KC; ++kc) {
-      uint32_t* hi = reinterpret_cast<uint32_t*>(out.data()) + ((size_t)nt * KC + kc) * 2 * PW;
-      uint32_t* lo = hi + PW;
+      __half* hi = base + ((size_t)nt * KC + kc) * 2 * PH;
+      __half* lo = hi + PH;
       for (int n = 0; n < BN; ++n)
         for (int k = 0; k < BKP; ++k) {
-          const float w = Bkn[(size_t)(kc * BKP + k) * ldb + nt * BN + n];
-          const uint32_t h = tf32_rna(w);
-          float hf; memcpy(&hf, &h, 4);
-          const uint32_t l = tf32_rna(w - hf);
-          const int off = (n >> 3) * 256 + (n & 7) * 32 + (((k >> 2) ^ (n & 7)) << 2) + (k & 3);   // in 4-byte words
+          const float w = Bkn[(size_t)(kc * BKP + k) * ldb + nt * BN + n] * sc;
+          const __half h = __float2half_rn(w);
+          const __half l = __float2half_rn(w - __half2float(h));
+          const int off = (n >> 3) * 512 + (n & 7) * 64 + (((k >> 3) ^ (n & 7)) << 3) + (k & 7);   // in fp16 elements
           hi[off] = h; lo[off] = l;
         }
     }

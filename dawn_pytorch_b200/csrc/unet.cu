@@ -43,7 +43,7 @@ struct Act {          // channels-last activation view: pixel stride ld, C chann
   float* p = nullptr; int ld = 0; int C = 0; int H = 0; int W = 0;
 };
 
-struct ConvW { float* w = nullptr; float* b = nullptr; float* img = nullptr; int K = 0, N = 0, ldb = 0; };
+struct ConvW { float* w = nullptr; float* b = nullptr; float* img = nullptr; float img_scale = 1.f; int K = 0, N = 0, ldb = 0; };
 
 struct CrossAttnW { float *Wkv, *nkv, *qs, *ks, *Wout, *gout; };
 
@@ -55,6 +55,7 @@ struct ResBlockW {
   float *gn1w = nullptr, *gn1b = nullptr, *gn2w = nullptr, *gn2b = nullptr;
   float *tW = nullptr, *tB = nullptr;
   float *mW[3] = {nullptr, nullptr, nullptr}, *mB[3] = {nullptr, nullptr, nullptr};   // pose, aud, eye MLPs
+  float Wq_scale = 1.f;
   float *Wq = nullptr, *wsumq = nullptr, *Wq_img = nullptr;                              // [ci][192], [192]
   CrossAttnW ca[3];
   // per-clip (depend on F / cond)
@@ -64,10 +65,10 @@ struct ResBlockW {
 };
 
 struct AttnW {     // temporal attention / mid spatial attention (U:648-725)
-  int C = 0; float *Wqkv = nullptr, *wsum = nullptr, *Wqkv_img = nullptr; ConvW out;
+  int C = 0; float Wqkv_scale = 1.f; float *Wqkv = nullptr, *wsum = nullptr, *Wqkv_img = nullptr; ConvW out;
 };
 struct SlaW {      // spatial linear attention (U:602-627)
-  int C = 0; float *Wqkv = nullptr, *wsum = nullptr, *Wqkv_img = nullptr, *WoutT = nullptr, *bout = nullptr;
+  int C = 0; float Wqkv_scale = 1.f; float *Wqkv = nullptr, *wsum = nullptr, *Wqkv_img = nullptr, *WoutT = nullptr, *bout = nullptr;
 };
 struct UpW { ConvW cls[4]; };
 
@@ -155,11 +156,11 @@ void free_all(std::vector<void*>& v) {
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // tcgen05 image of a [K][ldb] weight matrix (only for shapes the tcgen05 kernel accepts)
-int upload_tc_image(dawn_unet* h, const std::vector<float>& m, int K, int N, int ldb, float** img) {
-  *img = nullptr;
-  if (!h->use_tc || N % 64 != 0 || K % 32 != 0) return 0;
+int upload_tc_image(dawn_unet* h, const std::vector<float>& m, int K, int N, int ldb, float** img, float* scale) {
+  *img = nullptr; *scale = 1.f;
+  if (!h->use_tc || N % 64 != 0 || K % 64 != 0) return 0;
   std::vector<float> im;
-  tc_pack_weights(m.data(), K, N, ldb, im);
+  tc_pack_weights(m.data(), K, N, ldb, im, scale);
   return dev_upload(h, im, img);
 }
 
@@ -195,7 +196,7 @@ int pack_conv(dawn_unet* h, const std::string& prefix, int co, int ci, int kh, i
       for (int t = 0; t < kh * kw; ++t)
         m[((size_t)t * ci_pad + c) * ldb + n] = w->data[((size_t)n * ci + c) * kh * kw + t];
   DAWN_TRY(dev_upload(h, m, &out->w));
-  DAWN_TRY(upload_tc_image(h, m, K, co, ldb, &out->img));
+  DAWN_TRY(upload_tc_image(h, m, K, co, ldb, &out->img, &out->img_scale));
   out->b = nullptr;
   if (bias) {
     std::vector<float> bb(ldb, 0.f);
@@ -209,7 +210,7 @@ int pack_conv(dawn_unet* h, const std::string& prefix, int co, int ci, int kh, i
 // Linear weight (N, K) [+ optional per-input gain, + per-output-row scale for the first `nscale` rows]
 // -> [K][ldb], plus column sums for the LayerNorm fold
 int pack_linear(dawn_unet* h, const HostParam* w, int N, int K, const float* gain, float qscale, int nscale,
-                float** Wout, float** wsum, int* ldb_out, float** img = nullptr) {
+                float** Wout, float** wsum, int* ldb_out, float** img = nullptr, float* img_scale = nullptr) {
   const int ldb = round_up(N, 64);
   std::vector<float> m((size_t)K * ldb, 0.f), s(ldb, 0.f);
   for (int n = 0; n < N; ++n) {
@@ -225,7 +226,7 @@ int pack_linear(dawn_unet* h, const HostParam* w, int N, int K, const float* gai
     s[n] = (float)acc;
   }
   DAWN_TRY(dev_upload(h, m, Wout));
-  if (img) DAWN_TRY(upload_tc_image(h, m, K, N, ldb, img));
+  if (img) DAWN_TRY(upload_tc_image(h, m, K, N, ldb, img, img_scale));
   if (wsum) DAWN_TRY(dev_upload(h, s, wsum));
   if (ldb_out) *ldb_out = ldb;
   return 0;
@@ -282,7 +283,7 @@ int pack_resblock(dawn_unet* h, const std::string& name, int ci, int co, bool co
       DAWN_TRY(upload_raw(h, p + ".to_out.1.g", {co}, &r.ca[a].gout));
     }
     DAWN_TRY(dev_upload(h, wq, &r.Wq));
-    DAWN_TRY(upload_tc_image(h, wq, ci, 192, 192, &r.Wq_img));
+    DAWN_TRY(upload_tc_image(h, wq, ci, 192, 192, &r.Wq_img, &r.Wq_scale));
     DAWN_TRY(dev_upload(h, wsum, &r.wsumq));
   }
   h->rb_index[name] = (int)h->rb.size();
@@ -297,9 +298,9 @@ int pack_attn(dawn_unet* h, const std::string& norm_name, const std::string& fn,
   DAWN_TRY(need(h, fn + ".to_out.weight", {C, 256}, &o));
   a->C = C;
   const float scale = 1.0f / sqrtf(32.0f);                                   // q * dim_head^-0.5 (U:657, 687)
-  DAWN_TRY(pack_linear(h, qkv, 768, C, g->data.data(), scale, 256, &a->Wqkv, &a->wsum, nullptr, &a->Wqkv_img));
+  DAWN_TRY(pack_linear(h, qkv, 768, C, g->data.data(), scale, 256, &a->Wqkv, &a->wsum, nullptr, &a->Wqkv_img, &a->Wqkv_scale));
   int ldb = 0;
-  DAWN_TRY(pack_linear(h, o, C, 256, nullptr, 1.f, 0, &a->out.w, nullptr, &ldb, &a->out.img));
+  DAWN_TRY(pack_linear(h, o, C, 256, nullptr, 1.f, 0, &a->out.w, nullptr, &ldb, &a->out.img, &a->out.img_scale));
   a->out.b = nullptr; a->out.K = 256; a->out.N = C; a->out.ldb = ldb;
   return 0;
 }
@@ -311,7 +312,7 @@ int pack_sla(dawn_unet* h, const std::string& p, int C, SlaW* s) {        // p =
   DAWN_TRY(need(h, p + ".fn.to_out.weight", {C, 256, 1, 1}, &o));
   DAWN_TRY(need(h, p + ".fn.to_out.bias", {C}, &b));
   s->C = C;
-  DAWN_TRY(pack_linear(h, qkv, 768, C, g->data.data(), 1.f, 0, &s->Wqkv, &s->wsum, nullptr, &s->Wqkv_img));
+  DAWN_TRY(pack_linear(h, qkv, 768, C, g->data.data(), 1.f, 0, &s->Wqkv, &s->wsum, nullptr, &s->Wqkv_img, &s->Wqkv_scale));
   std::vector<float> wt((size_t)256 * C);
   for (int c = 0; c < C; ++c)
     for (int k = 0; k < 256; ++k) wt[(size_t)k * C + c] = o->data[(size_t)c * 256 + k];
@@ -347,7 +348,7 @@ int pack_up(dawn_unet* h, const std::string& name, int C, UpW* u) {
         }
       ConvW& cw = u->cls[py * 2 + px];
       DAWN_TRY(dev_upload(h, m, &cw.w));
-      DAWN_TRY(upload_tc_image(h, m, 4 * C, C, ldb, &cw.img));
+      DAWN_TRY(upload_tc_image(h, m, 4 * C, C, ldb, &cw.img, &cw.img_scale));
       cw.b = bdev; cw.K = 4 * C; cw.N = C; cw.ldb = ldb;
     }
   return 0;
@@ -365,7 +366,7 @@ void base_params(GemmParams& p, const Act& in, int F) {
   p.q_post_scale = 1.f;
 }
 void set_weights(GemmParams& p, const ConvW& w) {
-  p.B = w.w; p.Bimg = w.img; p.ldb = w.ldb; p.b_batch_stride = 0; p.N = w.N; p.K = w.K; p.bias = w.b;
+  p.B = w.w; p.Bimg = w.img; p.tc_scale = 1.0f / (kTcActScale * w.img_scale); p.ldb = w.ldb; p.b_batch_stride = 0; p.N = w.N; p.K = w.K; p.bias = w.b;
 }
 void set_square_taps(GemmParams& p, int k, int pad) {
   p.ntaps = k * k;
@@ -454,7 +455,7 @@ int resblock(Ctx& c, const ResBlockW& r, const Act& x, const Act& out) {
       DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
     }
     GemmParams p; base_params(p, x, F);
-    p.B = r.Wq; p.Bimg = r.Wq_img; p.ldb = 192; p.N = 192; p.K = r.ci;
+    p.B = r.Wq; p.Bimg = r.Wq_img; p.tc_scale = 1.0f / (kTcActScale * r.Wq_scale); p.ldb = 192; p.N = 192; p.K = r.ci;
     p.rowstats = h->ROWSTATS; p.wsum = r.wsumq; p.kq = r.kq; p.nkq = r.nkq; p.gates = h->GATES;
     DAWN_TRY(c.gemm(p, EPI_CA_GATE, PC_CA_GATE));
     ProfScope ps(c, PC_CA_RSTD, 0, 4.0 * M * 56);
@@ -503,7 +504,7 @@ int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const st
   }
   {
     GemmParams p; base_params(p, x, F);
-    p.B = w.Wqkv; p.Bimg = w.Wqkv_img; p.ldb = 768; p.N = 768; p.K = x.C;
+    p.B = w.Wqkv; p.Bimg = w.Wqkv_img; p.tc_scale = 1.0f / (kTcActScale * w.Wqkv_scale); p.ldb = 768; p.N = 768; p.K = x.C;
     p.rowstats = h->ROWSTATS; p.wsum = w.wsum; p.rot = h->ROT;
     p.Out = h->QKV; p.ldo = 768;
     DAWN_TRY(c.gemm(p, EPI_QKV_TEMPORAL, PC_QKV));
@@ -538,7 +539,7 @@ int mid_spatial_attn(Ctx& c, const AttnW& w, const Act& x, const std::string& na
   }
   {
     GemmParams p; base_params(p, x, F);
-    p.B = w.Wqkv; p.Bimg = w.Wqkv_img; p.ldb = 768; p.N = 768; p.K = x.C;
+    p.B = w.Wqkv; p.Bimg = w.Wqkv_img; p.tc_scale = 1.0f / (kTcActScale * w.Wqkv_scale); p.ldb = 768; p.N = 768; p.K = x.C;
     p.rowstats = h->ROWSTATS; p.wsum = w.wsum;
     p.Out = h->QKV; p.ldo = 768;
     DAWN_TRY(c.gemm(p, EPI_QKV_MID, PC_QKV));
@@ -571,7 +572,7 @@ int sla(Ctx& c, const SlaW& w, const Act& x, const std::string& name) {
   }
   {
     GemmParams p; base_params(p, x, F);
-    p.B = w.Wqkv; p.Bimg = w.Wqkv_img; p.ldb = 768; p.N = 768; p.K = x.C;
+    p.B = w.Wqkv; p.Bimg = w.Wqkv_img; p.tc_scale = 1.0f / (kTcActScale * w.Wqkv_scale); p.ldb = 768; p.N = 768; p.K = x.C;
     p.rowstats = h->ROWSTATS; p.wsum = w.wsum; p.q_post_scale = 1.0f / sqrtf(32.0f);
     p.Out = h->QKV; p.ldo = 768;
     DAWN_TRY(c.gemm(p, EPI_QKV_SLA, PC_QKV));
@@ -1080,7 +1081,8 @@ int dawn_selftest_tc_gemm(int F, int H, int W, int Cin, int N, int ksize, int wi
   for (int k = 0; k < K; ++k) for (int n = 0; n < N; ++n) hB[(size_t)k * ldb + n] = rnd() * 0.05f;
   for (int n = 0; n < N; ++n) hb[n] = rnd();
   std::vector<float> img;
-  tc_pack_weights(hB.data(), K, N, ldb, img);
+  float img_scale = 1.f;
+  tc_pack_weights(hB.data(), K, N, ldb, img, &img_scale);
   std::vector<void*> own;
   float *dA, *dB, *db, *dImg, *dO1, *dO2, *dS;
   auto cleanup = [&]() { free_all(own); };
@@ -1094,7 +1096,7 @@ int dawn_selftest_tc_gemm(int F, int H, int W, int Cin, int N, int ksize, int wi
   cudaMemset(dS, 0, 64 * 4);
   Act in{dA, Cin, Cin, H, W};
   GemmParams p; base_params(p, in, F);
-  p.B = dB; p.Bimg = dImg; p.ldb = ldb; p.N = N; p.K = K; p.bias = db;
+  p.B = dB; p.Bimg = dImg; p.tc_scale = 1.0f / (kTcActScale * img_scale); p.ldb = ldb; p.N = N; p.K = K; p.bias = db;
   set_square_taps(p, ksize, ksize / 2);
   if (with_stats) { p.stats = (double*)dS; p.cpg = N / 8; }
   p.Out = dO1; p.ldo = N;
