@@ -11,7 +11,7 @@ int tc_tile_n(int N);
 bool tc_gemm_supported(const GemmParams& p, int epi);
 // host: [K][ldb] fp32 -> pre-scaled, pre-split (fp16 hi | lo), pre-swizzled shared-memory images per (n-tile, k-panel)
 size_t tc_pack_weights(const float* Bkn, int K, int N, int ldb, std::vector<float>& out, float* scale);
-constexpr float kTcActScale = 8.0f;
+constexpr float kTcActScale = 1.0f;
 int launch_tc_gemm(const GemmParams& p, const float* Bimg, int epi, cudaStream_t st);
 
 }  // namespace dawn
