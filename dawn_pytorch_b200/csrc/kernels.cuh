@@ -62,7 +62,9 @@ struct AttnArgs {
   const float* bias;             // [8][2*band+1] or null
   int q_lo, q_hi;                // only queries in [q_lo, q_hi) are computed (frame sharding); keys span [0, L)
 };
-int launch_attention(const AttnArgs& a, cudaStream_t st);
+int launch_attention(const AttnArgs& a, cudaStream_t st);          // SIMT fp32 reference kernel
+bool attention_tc_supported(const AttnArgs& a);
+int launch_attention_tc(const AttnArgs& a, cudaStream_t st);       // tensor-core (mma.sync fp16x3) kernel, attn_tc.cu
 
 // spatial linear attention: per (frame, head) context + composed out-projection  U:618-626
 //   Bf[f][h*32+d][c] = sum_e ctx[f,h][d][e] * WoutT[h*32+e][c]

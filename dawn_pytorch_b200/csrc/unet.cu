@@ -85,6 +85,7 @@ struct dawn_unet {
   std::unordered_map<std::string, HostParam> raw;
   bool committed = false;
   bool use_tc = true;                          // tcgen05 contraction path (DAWN_TC=0 falls back to mma.sync)
+  bool use_attn_tc = true;                     // tensor-core attention core (DAWN_ATTN_TC=0 falls back to SIMT)
 
   // packed weights
   std::vector<void*> owned;                    // weight allocations
@@ -517,7 +518,8 @@ int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const st
     double pairs = 0;
     for (int i = 0; i < F; ++i) pairs += std::min(F - 1, i + a.band) - std::max(0, i - a.band) + 1;
     ProfScope ps(c, PC_ATTN_CORE, 4.0 * 32 * 8 * P * pairs, 4.0 * M * 1024);
-    DAWN_TRY(launch_attention(a, c.st));
+    if (h->use_attn_tc && attention_tc_supported(a)) DAWN_TRY(launch_attention_tc(a, c.st));
+    else DAWN_TRY(launch_attention(a, c.st));
   }
   {
     Act o{h->O, 256, 256, x.H, x.W};
@@ -550,7 +552,8 @@ int mid_spatial_attn(Ctx& c, const AttnW& w, const Act& x, const std::string& na
     a.nseq = F; a.L = P; a.seq_base_stride = P; a.elem_stride = 1;
     a.band = 1 << 30; a.bias = nullptr; a.q_lo = 0; a.q_hi = P;
     ProfScope ps(c, PC_ATTN_CORE, 4.0 * 32 * 8 * (double)F * P * P, 4.0 * M * 1024);
-    DAWN_TRY(launch_attention(a, c.st));
+    if (h->use_attn_tc && attention_tc_supported(a)) DAWN_TRY(launch_attention_tc(a, c.st));
+    else DAWN_TRY(launch_attention(a, c.st));
   }
   {
     Act o{h->O, 256, 256, x.H, x.W};
@@ -752,6 +755,7 @@ int dawn_unet_create(const dawn_unet_cfg* cfg, dawn_unet** out) {
   dawn_unet* h = new dawn_unet();
   h->cfg = *cfg;
   { const char* e = getenv("DAWN_TC"); h->use_tc = !(e && e[0] == '0'); }
+  { const char* e = getenv("DAWN_ATTN_TC"); h->use_attn_tc = !(e && e[0] == '0'); }
   h->nlev = cfg->n_levels;
   h->dims.push_back(cfg->dim);
   for (int i = 0; i < cfg->n_levels; ++i) h->dims.push_back(cfg->dim * cfg->dim_mults[i]);
@@ -1069,6 +1073,50 @@ int dawn_unet_profile_read(dawn_unet* h, double* ms, double* flops, double* byte
   return 0;
 }
 int64_t dawn_unet_workspace_bytes(dawn_unet* h) { return h ? h->ws_bytes : 0; }
+
+// random qkv through both attention kernels (temporal: nseq pixel sequences of L frames, band 40 + bias;
+// spatial: nseq frames of L tokens, full attention); reports max |tensor-core - SIMT|
+int dawn_selftest_attention(int nseq, int L, int temporal, float* max_abs_diff, float* max_abs_ref) {
+  DAWN_CHECK(max_abs_diff && max_abs_ref, "null argument");
+  const size_t rows = (size_t)nseq * L;
+  std::vector<float> hq(rows * 768), hb(8 * 81);
+  uint32_t seed = 777u;
+  auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return ((seed >> 8) & 0xFFFF) / 32768.0f - 1.0f; };
+  for (auto& v : hq) v = rnd() * 1.5f;
+  for (auto& v : hb) v = rnd() * 2.0f;
+  std::vector<void*> own;
+  float *dq, *db, *o1, *o2;
+  if (dev_alloc(own, hq.size(), &dq) || dev_alloc(own, hb.size(), &db) || dev_alloc(own, rows * 256, &o1) || dev_alloc(own, rows * 256, &o2)) {
+    free_all(own); return -2;
+  }
+  cudaMemcpy(dq, hq.data(), hq.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(db, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemset(o1, 0, rows * 256 * 4); cudaMemset(o2, 0, rows * 256 * 4);
+  AttnArgs a{};
+  a.qkv = dq; a.ld = 768; a.ldo = 256; a.nseq = nseq; a.L = L;
+  if (temporal) { a.seq_base_stride = 1; a.elem_stride = nseq; a.band = 40; a.bias = db; }
+  else { a.seq_base_stride = L; a.elem_stride = 1; a.band = 1 << 30; a.bias = nullptr; }
+  a.q_lo = 0; a.q_hi = L;
+  a.out = o1;
+  int rc = launch_attention(a, 0);
+  a.out = o2;
+  if (rc == 0) rc = launch_attention_tc(a, 0);
+  if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) { set_last_error(std::string("selftest: ") + cudaGetErrorString(cudaGetLastError())); rc = -2; }
+  if (rc == 0) {
+    std::vector<float> r1(rows * 256), r2(rows * 256);
+    cudaMemcpy(r1.data(), o1, r1.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(r2.data(), o2, r2.size() * 4, cudaMemcpyDeviceToHost);
+    float md = 0.f, mr = 0.f;
+    for (size_t i = 0; i < r1.size(); ++i) {
+      const float d = std::fabs(r1[i] - r2[i]);
+      md = (d > md || d != d) ? d : md;
+      mr = std::max(mr, std::fabs(r1[i]));
+    }
+    *max_abs_diff = md; *max_abs_ref = mr;
+  }
+  free_all(own);
+  return rc;
+}
 
 // random k x k conv through both contraction kernels; reports max |tcgen05 - mma.sync| over outputs and GN statistics
 int dawn_selftest_tc_gemm(int F, int H, int W, int Cin, int N, int ksize, int with_stats, float* max_abs_diff, float* max_abs_ref) {

@@ -100,6 +100,10 @@ int64_t dawn_unet_workspace_bytes(dawn_unet* h);
  * (F frames of H x W, Cin -> N channels); reports max |difference| (outputs and, if requested, GroupNorm sums). */
 int dawn_selftest_tc_gemm(int F, int H, int W, int Cin, int N, int ksize, int with_stats, float* max_abs_diff, float* max_abs_ref);
 
+/* self-test of the tensor-core attention core against the SIMT fp32 kernel on random q/k/v:
+ * temporal != 0: nseq pixel sequences of L frames, band 40 with bias; else nseq frames of L tokens, full attention */
+int dawn_selftest_attention(int nseq, int L, int temporal, float* max_abs_diff, float* max_abs_ref);
+
 const char* dawn_last_error(void);
 const char* dawn_build_info(void);
 
