@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(AttnArgs a) {
   const int q1 = min(q0 + QSPAN, a.q_hi);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const long long base = (long long)seq * a.seq_base_stride;
+  const long long base = attn_seq_base(a, seq);
+  const long long estride = attn_elem_stride(a);
   const int band = a.band;
   const bool banded = band < a.L;
 
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(AttnArgs a) {
         const int col = ks * 16 + 2 * t + ((r & 2) ? 8 : 0);
         float2 v = make_float2(0.f, 0.f);
         if (row < q1)
-          v = *reinterpret_cast<const float2*>(a.qkv + (size_t)(base + (long long)row * a.elem_stride) * a.ld + head * 32 + col);
+          v = *reinterpret_cast<const float2*>(a.qkv + (size_t)(base + (long long)row * estride) * a.ld + head * 32 + col);
         split2(v.x, v.y, qh[b][ks][r], ql[b][ks][r]);
       }
     }
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(AttnArgs a) {
       const int key = kc0 + r;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < nk && key >= 0 && key < a.L)
-        v = *reinterpret_cast<const float4*>(a.qkv + (size_t)(base + (long long)key * a.elem_stride) * a.ld + 256 + (c >> 3) * 256 +
+        v = *reinterpret_cast<const float4*>(a.qkv + (size_t)(base + (long long)key * estride) * a.ld + 256 + (c >> 3) * 256 +
                                              head * 32 + (c & 7) * 4);
       if (c < 8) {
         uint32_t h0, l0, h1, l1;
@@ -235,10 +236,10 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(AttnArgs a) {
     for (int n = 0; n < 4; ++n) {
       const int col = head * 32 + n * 8 + 2 * t;
       if (r0 < q1)
-        *reinterpret_cast<float2*>(a.out + (size_t)(base + (long long)r0 * a.elem_stride) * a.ldo + col) =
+        *reinterpret_cast<float2*>(a.out + (size_t)(base + (long long)r0 * estride) * a.ldo + col) =
             make_float2(o[b][n][0] * inv0, o[b][n][1] * inv0);
       if (r1 < q1)
-        *reinterpret_cast<float2*>(a.out + (size_t)(base + (long long)r1 * a.elem_stride) * a.ldo + col) =
+        *reinterpret_cast<float2*>(a.out + (size_t)(base + (long long)r1 * estride) * a.ldo + col) =
             make_float2(o[b][n][2] * inv1, o[b][n][3] * inv1);
     }
   }

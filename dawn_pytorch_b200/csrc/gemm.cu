@@ -57,7 +57,9 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_kernel(const GemmParams p) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     int m = m0 + (tid >> 3) + 32 * q;
-    if (m < m_end) {
+    if (m < m_end && p.perm_in) {
+      a_pix[q] = seq_blocked_pixel(m, p.perm_pb, p.perm_F, p.P); a_iy[q] = 0; a_ix[q] = 0;
+    } else if (m < m_end) {
       int f = m / Ps, rem = m - f * Ps;
       int i = rem / p.OWs, j = rem - i * p.OWs;
       a_pix[q] = f * p.IH * p.IW;
@@ -164,7 +166,9 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_kernel(const GemmParams p) {
       const int f = mc / Ps;
       const int rem = mc - f * Ps;
       const int oi = rem / p.OWs, oj = rem - oi * p.OWs;
-      const size_t opix = (size_t)(f * p.OH + oi * p.out_stride + p.oy0) * p.OW + oj * p.out_stride + p.ox0;
+      const size_t opix = p.perm_out ? (size_t)seq_blocked_pixel(mc, p.perm_pb, p.perm_F, p.P)
+                                     : (size_t)(f * p.OH + oi * p.out_stride + p.oy0) * p.OW + oj * p.out_stride + p.ox0;
+      const int srow = p.perm_in ? seq_blocked_pixel(mc, p.perm_pb, p.perm_F, p.P) : mc;   // pixel behind this row
       float v[4][2];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_kernel(const GemmParams p) {
         }
       } else {
         // LayerNorm fold: W(gamma .* (x-mu)*rstd) = rstd * (W' x - mu * rowsum(W'))
-        const float mu = p.rowstats[2 * mc], rs = p.rowstats[2 * mc + 1];
+        const float mu = p.rowstats[2 * (size_t)srow], rs = p.rowstats[2 * (size_t)srow + 1];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int n = ncol0 + nt * 8;
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_kernel(const GemmParams p) {
           v[nt][1] = rs * (v[nt][1] - mu * p.wsum[n + 1]);
         }
         if (EPI == EPI_QKV_TEMPORAL) {
-          const int fr = mc / p.P;
+          const int fr = srow / p.P;
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) {
             const int n = ncol0 + nt * 8;

@@ -26,6 +26,10 @@ struct GemmParams {
   int ntaps; signed char dy[52]; signed char dx[52];
   int M, N, K;             // K = ntaps * Cin (multiple of 32)
   int rows_per_batch;      // rows sharing one B matrix (P for per-frame weights, else M)
+  // sequence-blocked row order for temporal attention (1x1 problems only): row m = ((p / pb) * F + f) * pb + p % pb
+  // stands for pixel f * P + p.  perm_in: the A operand / LayerNorm statistics / rotary frame of row m come from that
+  // pixel; perm_out: output and residual of row m go to that pixel.  pb = 0 disables.
+  int perm_pb, perm_F, perm_in, perm_out;
   // B operand [K][ldb] (ldb multiple of 64, zero padded)
   const float* B; int ldb; long long b_batch_stride;
   const float* Bimg;       // optional tcgen05 image of B (tc_pack_weights), or null
@@ -51,6 +55,13 @@ struct GemmParams {
   double gn_count;         // elements per group
   unsigned long long* trace;   // optional [16] cycle counters written by CTA 0 of the tcgen05 kernel (debug)
 };
+
+// pixel index (f * P + p) of row m in sequence-blocked order
+__host__ __device__ inline int seq_blocked_pixel(int m, int pb, int F, int P) {
+  const int blk = m / (F * pb), rem = m - blk * F * pb;
+  const int f = rem / pb, pi = rem - f * pb;
+  return f * P + blk * pb + pi;
+}
 
 int launch_gemm(const GemmParams& p, int epi, cudaStream_t st);
 

@@ -363,14 +363,15 @@ __global__ void __launch_bounds__(128) attention_kernel(AttnArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int iq = q0 + warp * 32 + lane;
   const bool qv = iq < a.q_hi;
-  const long long base = (long long)seq * a.seq_base_stride;
+  const long long base = attn_seq_base(a, seq);
+  const long long estride = attn_elem_stride(a);
   const int band = a.band;
   const bool banded = band < a.L;
 
   float q[32], o[32];
   {
     const int ic = qv ? iq : a.q_lo;
-    const float4* qp = reinterpret_cast<const float4*>(a.qkv + (size_t)(base + (long long)ic * a.elem_stride) * a.ld + head * 32);
+    const float4* qp = reinterpret_cast<const float4*>(a.qkv + (size_t)(base + (long long)ic * estride) * a.ld + head * 32);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float4 t = qp[k];
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(128) attention_kernel(AttnArgs a) {
     __syncthreads();
     for (int idx = threadIdx.x; idx < nk * 16; idx += blockDim.x) {
       const int r = idx >> 4, c = idx & 15;      // c < 8: K, else V
-      const float* src = a.qkv + (size_t)(base + (long long)(kc0 + r) * a.elem_stride) * a.ld + 256 + (c >> 3) * 256 + head * 32 + (c & 7) * 4;
+      const float* src = a.qkv + (size_t)(base + (long long)(kc0 + r) * estride) * a.ld + 256 + (c >> 3) * 256 + head * 32 + (c & 7) * 4;
       const float4 t = *reinterpret_cast<const float4*>(src);
       float* dst = (c < 8) ? &Ks[r][(c & 7) * 4] : &Vs[r][(c & 7) * 4];
       *reinterpret_cast<float4*>(dst) = t;
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(128) attention_kernel(AttnArgs a) {
   }
   if (qv) {
     const float inv = 1.0f / lrun;
-    float4* op = reinterpret_cast<float4*>(a.out + (size_t)(base + (long long)iq * a.elem_stride) * a.ldo + head * 32);
+    float4* op = reinterpret_cast<float4*>(a.out + (size_t)(base + (long long)iq * estride) * a.ldo + head * 32);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       op[k] = make_float4(o[4 * k] * inv, o[4 * k + 1] * inv, o[4 * k + 2] * inv, o[4 * k + 3] * inv);

@@ -61,7 +61,12 @@ struct AttnArgs {
   int band;                      // |i-j| <= band attend; >= L means full
   const float* bias;             // [8][2*band+1] or null
   int q_lo, q_hi;                // only queries in [q_lo, q_hi) are computed (frame sharding); keys span [0, L)
+  int pb;                        // > 0: sequence-blocked rows: element e of sequence s is row ((s / pb) * L + e) * pb + s % pb
 };
+__host__ __device__ inline long long attn_seq_base(const AttnArgs& a, int s) {
+  return a.pb > 0 ? (long long)(s / a.pb) * a.L * a.pb + (s % a.pb) : (long long)s * a.seq_base_stride;
+}
+__host__ __device__ inline long long attn_elem_stride(const AttnArgs& a) { return a.pb > 0 ? a.pb : a.elem_stride; }
 int launch_attention(const AttnArgs& a, cudaStream_t st);          // SIMT fp32 reference kernel
 bool attention_tc_supported(const AttnArgs& a);
 int launch_attention_tc(const AttnArgs& a, cudaStream_t st);       // tensor-core (mma.sync fp16x3) kernel, attn_tc.cu

@@ -138,7 +138,7 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, ui
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-struct RowInfo { int pix; short iy, ix; };     // per tile row: input frame base pixel, top-left input coordinate
+struct RowInfo { int pix; int iy, ix; };     // per tile row: input frame base pixel, top-left input coordinate
 
 template <int EPI, int BN>
 __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const GemmParams p, const float* __restrict__ Bimg, int KC,
@@ -187,10 +187,12 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
       if (tid < BM) {
         const int m = m0 + tid;
         RowInfo ri;
-        if (m < p.M) {
+        if (m < p.M && p.perm_in) {
+          ri.pix = seq_blocked_pixel(m, p.perm_pb, p.perm_F, p.P); ri.iy = 0; ri.ix = 0;
+        } else if (m < p.M) {
           const int f = m / Ps, rem = m - f * Ps;
           const int i = rem / p.OWs, j = rem - i * p.OWs;
-          ri.pix = f * p.IH * p.IW; ri.iy = (short)(i * p.in_stride); ri.ix = (short)(j * p.in_stride);
+          ri.pix = f * p.IH * p.IW; ri.iy = i * p.in_stride; ri.ix = j * p.in_stride;
         } else {
           ri.pix = -1; ri.iy = 0; ri.ix = 0;
         }
@@ -390,7 +392,9 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
       const int mc = rv ? m : (p.M - 1);
       const int f = mc / Ps, rem = mc - f * Ps;
       const int oi = rem / p.OWs, oj = rem - oi * p.OWs;
-      const size_t opix = (size_t)(f * p.OH + oi * p.out_stride + p.oy0) * p.OW + oj * p.out_stride + p.ox0;
+      const size_t opix = p.perm_out ? (size_t)seq_blocked_pixel(mc, p.perm_pb, p.perm_F, p.P)
+                                     : (size_t)(f * p.OH + oi * p.out_stride + p.oy0) * p.OW + oj * p.out_stride + p.ox0;
+      const int srow = p.perm_in ? seq_blocked_pixel(mc, p.perm_pb, p.perm_F, p.P) : mc;     // pixel behind this row
 
       if (EPI == EPI_PLAIN) {
         if (p.bias) {
@@ -437,12 +441,12 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
         }
       } else {
         // LayerNorm fold (see gemm.cu): v = rstd * (acc - mu * colsum)
-        const float mu = p.rowstats[2 * (size_t)mc], rs = p.rowstats[2 * (size_t)mc + 1];
+        const float mu = p.rowstats[2 * (size_t)srow], rs = p.rowstats[2 * (size_t)srow + 1];
 #pragma unroll
         for (int i = 0; i < EN; ++i) acc[i] = rs * (acc[i] - mu * p.wsum[n0 + i]);
         if (EPI == EPI_QKV_TEMPORAL) {
           if (n0 < 512) {
-            const int fr = mc / p.P;
+            const int fr = srow / p.P;
 #pragma unroll
             for (int i = 0; i < EN; i += 2) {
               const int pi = ((n0 + i) & 31) >> 1;

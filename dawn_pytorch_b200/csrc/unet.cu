@@ -495,10 +495,17 @@ int resblock(Ctx& c, const ResBlockW& r, const Act& x, const Act& out) {
   return tap(c, r.name, out);
 }
 
+// largest divisor of P that is <= 16: pixel-block size of the sequence-blocked row order
+inline int seq_block(int P) { for (int b = 16; b > 1; --b) if (P % b == 0) return b; return 1; }
+
 // Residual(PreNorm(temporal Attention)) (U:648-725 / LA:275-342): x -> dst = x + to_out(attn(...))
+// q/k/v and the attention output live in SEQUENCE-BLOCKED row order (16 adjacent pixels x all frames contiguous):
+// with frame-major rows every (pixel, head) sequence touched one 2 MB page per frame and the attention core was
+// TLB/latency-bound; the QKV GEMM gathers its A rows through the permutation and the out-projection scatters back.
 int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const std::string& name) {
   dawn_unet* h = c.h;
   const int F = h->F, P = x.H * x.W, M = F * P;
+  const int pb = seq_block(P);
   {
     ProfScope ps(c, PC_ROWSTATS, 0, 4.0 * M * x.C);
     DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
@@ -508,12 +515,15 @@ int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const st
     p.B = w.Wqkv; p.Bimg = w.Wqkv_img; p.tc_scale = 1.0f / (kTcActScale * w.Wqkv_scale); p.ldb = 768; p.N = 768; p.K = x.C;
     p.rowstats = h->ROWSTATS; p.wsum = w.wsum; p.rot = h->ROT;
     p.Out = h->QKV; p.ldo = 768;
+    p.perm_pb = pb; p.perm_F = F; p.perm_in = 1; p.perm_out = 0;
+    // output rows are written in plain order m (the permuted enumeration): treat the output as one M x 1 "image"
+    p.OH = M; p.OW = 1; p.OHs = M; p.OWs = 1; p.IH = M; p.IW = 1;
     DAWN_TRY(c.gemm(p, EPI_QKV_TEMPORAL, PC_QKV));
   }
   {
     AttnArgs a{};
     a.qkv = h->QKV; a.ld = 768; a.out = h->O; a.ldo = 256;
-    a.nseq = P; a.L = F; a.seq_base_stride = 1; a.elem_stride = P;
+    a.nseq = P; a.L = F; a.seq_base_stride = 1; a.elem_stride = P; a.pb = pb;
     a.band = h->cfg.win_width; a.bias = h->rel_bias; a.q_lo = 0; a.q_hi = F;
     double pairs = 0;
     for (int i = 0; i < F; ++i) pairs += std::min(F - 1, i + a.band) - std::max(0, i - a.band) + 1;
@@ -522,9 +532,11 @@ int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const st
     else DAWN_TRY(launch_attention(a, c.st));
   }
   {
-    Act o{h->O, 256, 256, x.H, x.W};
-    GemmParams p; base_params(p, o, F);
+    Act o{h->O, 256, 256, M, 1};
+    GemmParams p; base_params(p, o, 1);
     set_weights(p, w.out);
+    p.P = P;
+    p.perm_pb = pb; p.perm_F = F; p.perm_in = 0; p.perm_out = 1;
     p.Res = x.p; p.ldr = x.ld; p.Out = dst.p; p.ldo = dst.ld;
     DAWN_TRY(c.gemm(p, EPI_PLAIN, PC_OUTPROJ));
   }
