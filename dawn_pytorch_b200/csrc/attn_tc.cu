@@ -2,7 +2,7 @@
 // block's full spatial attention U:841-843): FlashAttention-2 style, warp-level mma.sync m16n8k16 with the same
 // 3-term split as the contraction kernels (fp16 hi/lo pieces, fp32 accumulate) so that scores and outputs keep
 // fp32-level parity.
-//   CTA = (sequence, head, span of 128 queries); 4 warps, each owns 16-query blocks.
+//   CTA = (sequence, head, span of 128 queries); 8 warps, each owns one 16-query block.
 //   Keys/values of the span (banded: 128 + 2*band <= 208 keys; full: streamed in chunks of 192) are split once into
 //   fp16 hi/lo in shared memory: K row-major [key][d], V transposed [d][key] (B-operand layouts, padded against bank
 //   conflicts).  S = Q K^T per 32-key block -> + bias, band mask -> online softmax (fp32) -> P (accumulator layout
@@ -42,7 +42,9 @@ __device__ __forceinline__ void split1(float x, __half& hi, __half& lo) {
   lo = __float2half_rn(x - h);
 }
 
-__global__ void __launch_bounds__(128) attention_tc_kernel(AttnArgs a) {
+constexpr int ATHREADS = 256;
+
+__global__ void __launch_bounds__(ATHREADS) attention_tc_kernel(AttnArgs a) {
   extern __shared__ __align__(16) unsigned char att_smem[];
   __half* sKh = reinterpret_cast<__half*>(att_smem);
   __half* sKl = sKh + KROWS * K_LD;
@@ -61,16 +63,16 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(AttnArgs a) {
   const bool banded = band < a.L;
 
   if (a.bias != nullptr) {
-    for (int i = tid; i < 2 * band + 1 && i < 256; i += 128) s_bias[i] = a.bias[head * (2 * band + 1) + i];
+    for (int i = tid; i < 2 * band + 1 && i < 256; i += ATHREADS) s_bias[i] = a.bias[head * (2 * band + 1) + i];
   }
 
-  // this warp's query blocks: qb = warp, warp + 4 (16 queries each)
-  constexpr int NQB = QSPAN / 16 / 4;    // 2 per warp
+  // this warp's query block(s): qb = warp + 8 b (16 queries each)
+  constexpr int NQB = QSPAN / 16 / (ATHREADS / 32);    // 1 per warp
   uint32_t qh[NQB][2][4], ql[NQB][2][4];
   float o[NQB][4][4], mrow[NQB][2], lrow[NQB][2];
 #pragma unroll
   for (int b = 0; b < NQB; ++b) {
-    const int i0 = q0 + (warp + 4 * b) * 16;
+    const int i0 = q0 + (warp + (ATHREADS / 32) * b) * 16;
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
@@ -100,28 +102,41 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(AttnArgs a) {
   for (int kc0 = klo_all; kc0 < khi_all; kc0 += kstep) {
     const int nk = min(kstep, khi_all - kc0);                      // key rows of this chunk (multiple of 16 when banded)
     __syncthreads();
-    // ---- stage K (row-major) and V (transposed), split into fp16 hi/lo
-    for (int idx = tid; idx < KROWS * 16; idx += 128) {
-      const int r = idx >> 4, c = idx & 15;                        // c < 8: K float4 #c, else V float4 #(c-8)
-      const int key = kc0 + r;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < nk && key >= 0 && key < a.L)
-        v = *reinterpret_cast<const float4*>(a.qkv + (size_t)(base + (long long)key * estride) * a.ld + 256 + (c >> 3) * 256 +
-                                             head * 32 + (c & 7) * 4);
-      if (c < 8) {
-        uint32_t h0, l0, h1, l1;
-        split2(v.x, v.y, h0, l0); split2(v.z, v.w, h1, l1);
-        *reinterpret_cast<uint2*>(&sKh[r * K_LD + c * 4]) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(&sKl[r * K_LD + c * 4]) = make_uint2(l0, l1);
-      } else {
-        const int d = (c - 8) * 4;
-        const float vv[4] = {v.x, v.y, v.z, v.w};
+    // ---- stage K (row-major) and V (transposed), split into fp16 hi/lo; global loads issued in batches of 7
+    constexpr int ITEMS = KROWS * 16, BATCH = 7;
+    static_assert(ITEMS % (ATHREADS * BATCH) == 0, "staging loop assumes full batches");
+    for (int it0 = 0; it0 < ITEMS; it0 += ATHREADS * BATCH) {
+      float4 vb[BATCH];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __half hh, ll;
-          split1(vv[i], hh, ll);
-          sVh[(d + i) * V_LD + r] = hh;
-          sVl[(d + i) * V_LD + r] = ll;
+      for (int u = 0; u < BATCH; ++u) {
+        const int idx = it0 + u * ATHREADS + tid;
+        const int r = idx >> 4, c = idx & 15;                      // c < 8: K float4 #c, else V float4 #(c-8)
+        const int key = kc0 + r;
+        vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nk && key >= 0 && key < a.L)
+          vb[u] = __ldg(reinterpret_cast<const float4*>(a.qkv + (size_t)(base + (long long)key * estride) * a.ld + 256 + (c >> 3) * 256 +
+                                                        head * 32 + (c & 7) * 4));
+      }
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {
+        const int idx = it0 + u * ATHREADS + tid;
+        const int r = idx >> 4, c = idx & 15;
+        const float4 v = vb[u];
+        if (c < 8) {
+          uint32_t h0, l0, h1, l1;
+          split2(v.x, v.y, h0, l0); split2(v.z, v.w, h1, l1);
+          *reinterpret_cast<uint2*>(&sKh[r * K_LD + c * 4]) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(&sKl[r * K_LD + c * 4]) = make_uint2(l0, l1);
+        } else {
+          const int d = (c - 8) * 4;
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __half hh, ll;
+            split1(vv[i], hh, ll);
+            sVh[(d + i) * V_LD + r] = hh;
+            sVl[(d + i) * V_LD + r] = ll;
+          }
         }
       }
     }
@@ -129,7 +144,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(AttnArgs a) {
 
 #pragma unroll
     for (int b = 0; b < NQB; ++b) {
-      const int i0 = q0 + (warp + 4 * b) * 16;
+      const int i0 = q0 + (warp + (ATHREADS / 32) * b) * 16;
       if (i0 >= q1) continue;
       // 32-key blocks this query block needs inside the chunk
       int kb_lo = 0, kb_hi = (nk + 31) / 32;
@@ -226,7 +241,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(AttnArgs a) {
   // ---- normalise and store
 #pragma unroll
   for (int b = 0; b < NQB; ++b) {
-    const int i0 = q0 + (warp + 4 * b) * 16;
+    const int i0 = q0 + (warp + (ATHREADS / 32) * b) * 16;
     float l0 = lrow[b][0], l1 = lrow[b][1];
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
@@ -262,7 +277,7 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
     attr = true;
   }
   dim3 grid(a.nseq, 8, (a.q_hi - a.q_lo + QSPAN - 1) / QSPAN);
-  attention_tc_kernel<<<grid, 128, SMEM, st>>>(a);
+  attention_tc_kernel<<<grid, ATHREADS, SMEM, st>>>(a);
   DAWN_LAUNCH_OK();
   return 0;
 }
