@@ -161,12 +161,17 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_kernel(const GemmParams p) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int m = m0 + wm * 32 + mt * 16 + g + 8 * h;
-      const bool rv = m < m_end;
+      bool rv = m < m_end;
       const int mc = rv ? m : m0;     // clamp for address math; stores are predicated
+      int opx = 0;
+      if (p.perm_out) {
+        opx = seq_blocked_out_pixel(mc, p.perm_pb, p.perm_F, p.P, p.perm_f_lo, p.perm_f_hi);
+        if (opx < 0) { rv = false; opx = 0; }
+      }
       const int f = mc / Ps;
       const int rem = mc - f * Ps;
       const int oi = rem / p.OWs, oj = rem - oi * p.OWs;
-      const size_t opix = p.perm_out ? (size_t)seq_blocked_pixel(mc, p.perm_pb, p.perm_F, p.P)
+      const size_t opix = p.perm_out ? (size_t)opx
                                      : (size_t)(f * p.OH + oi * p.out_stride + p.oy0) * p.OW + oj * p.out_stride + p.ox0;
       const int srow = p.perm_in ? seq_blocked_pixel(mc, p.perm_pb, p.perm_F, p.P) : mc;   // pixel behind this row
       float v[4][2];

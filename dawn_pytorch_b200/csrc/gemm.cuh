@@ -30,6 +30,7 @@ struct GemmParams {
   // stands for pixel f * P + p.  perm_in: the A operand / LayerNorm statistics / rotary frame of row m come from that
   // pixel; perm_out: output and residual of row m go to that pixel.  pb = 0 disables.
   int perm_pb, perm_F, perm_in, perm_out;
+  int perm_f_lo, perm_f_hi;  // perm_out only: rows whose frame f lies outside [f_lo, f_hi) are dropped, the rest go to frame f - f_lo
   // B operand [K][ldb] (ldb multiple of 64, zero padded)
   const float* B; int ldb; long long b_batch_stride;
   const float* Bimg;       // optional tcgen05 image of B (tc_pack_weights), or null
@@ -61,6 +62,13 @@ __host__ __device__ inline int seq_blocked_pixel(int m, int pb, int F, int P) {
   const int blk = m / (F * pb), rem = m - blk * F * pb;
   const int f = rem / pb, pi = rem - f * pb;
   return f * P + blk * pb + pi;
+}
+// same, for an output restricted to frames [f_lo, f_hi): returns -1 for rows of other (halo) frames
+__host__ __device__ inline int seq_blocked_out_pixel(int m, int pb, int F, int P, int f_lo, int f_hi) {
+  const int blk = m / (F * pb), rem = m - blk * F * pb;
+  const int f = rem / pb, pi = rem - f * pb;
+  if (f < f_lo || f >= f_hi) return -1;
+  return (f - f_lo) * P + blk * pb + pi;
 }
 
 int launch_gemm(const GemmParams& p, int epi, cudaStream_t st);

@@ -388,11 +388,16 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
       const bool tr_e = (p.trace != nullptr) && blockIdx.x == 0 && etid == 0;
       const long long te0 = tr_e ? clock64() : 0;
       const int m = m0 + row_in_tile;
-      const bool rv = m < p.M;
+      bool rv = m < p.M;
       const int mc = rv ? m : (p.M - 1);
+      int opx = 0;
+      if (p.perm_out) {
+        opx = seq_blocked_out_pixel(mc, p.perm_pb, p.perm_F, p.P, p.perm_f_lo, p.perm_f_hi);
+        if (opx < 0) { rv = false; opx = 0; }
+      }
       const int f = mc / Ps, rem = mc - f * Ps;
       const int oi = rem / p.OWs, oj = rem - oi * p.OWs;
-      const size_t opix = p.perm_out ? (size_t)seq_blocked_pixel(mc, p.perm_pb, p.perm_F, p.P)
+      const size_t opix = p.perm_out ? (size_t)opx
                                      : (size_t)(f * p.OH + oi * p.out_stride + p.oy0) * p.OW + oj * p.out_stride + p.ox0;
       const int srow = p.perm_in ? seq_blocked_pixel(mc, p.perm_pb, p.perm_F, p.P) : mc;     // pixel behind this row
 

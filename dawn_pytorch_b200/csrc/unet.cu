@@ -1,6 +1,7 @@
 // Host-side orchestration + C-ABI of the DAWN denoising UNet (reference U:728-965; see include/dawn_unet.h).
 // One handle = one GPU = one clip at a time.  Weights are repacked once into GEMM-friendly layouts;
 // activations live channels-last (F, H, W, C) in a workspace sized by dawn_unet_set_num_frames.
+#include <dlfcn.h>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -31,6 +32,50 @@ void set_last_error(const std::string& s) { g_last_error = s; }
   do {                           \
     int _rc = (expr);            \
     if (_rc != 0) return _rc;    \
+  } while (0)
+
+// ------------------------------------------------------------------ NCCL, resolved at run time (torch ships libnccl.so.2)
+typedef struct ncclComm* ncclComm_t;
+struct NcclUniqueId { char internal[128]; };
+struct NcclApi {
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, NcclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0;
+static NcclApi g_nccl;
+static int load_nccl() {
+  if (g_nccl.ok) return 0;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) { set_last_error(std::string("cannot load libnccl.so.2: ") + dlerror()); return -1; }
+#define DAWN_NCCL_SYM(field, name)                                                        \
+  g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(lib, name));              \
+  if (!g_nccl.field) { set_last_error(std::string("libnccl lacks ") + name); return -1; }
+  DAWN_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+  DAWN_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+  DAWN_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  DAWN_NCCL_SYM(AllReduce, "ncclAllReduce")
+  DAWN_NCCL_SYM(Send, "ncclSend")
+  DAWN_NCCL_SYM(Recv, "ncclRecv")
+  DAWN_NCCL_SYM(GroupStart, "ncclGroupStart")
+  DAWN_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+  DAWN_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef DAWN_NCCL_SYM
+  g_nccl.ok = true;
+  return 0;
+}
+#define DAWN_NCCL_OK(expr)                                                                                   \
+  do {                                                                                                       \
+    int _r = (expr);                                                                                         \
+    if (_r != 0) { ::dawn::set_last_error(std::string(#expr) + ": " + g_nccl.GetErrorString(_r)); return -2; } \
   } while (0)
 
 struct HostParam {
@@ -117,6 +162,11 @@ struct dawn_unet {
   int64_t* T_HOSTSIDE = nullptr;               // device int64 for forward_host
   float *H_XT = nullptr, *H_FEA = nullptr, *H_COND = nullptr, *H_OUT = nullptr;   // device staging for forward_host
   bool have_invariants = false;
+
+  // frame sharding of one clip across ranks (exact: per-layer halo exchange + GroupNorm all-reduce)
+  int sh_nranks = 1, sh_rank = 0, sh_Fglobal = 0, sh_halo_l = 0, sh_halo_r = 0;
+  ncclComm_t sh_comm = nullptr;
+  float* XE = nullptr;                         // (halo_l + F + halo_r) frames of a temporal layer's input, dense
 
   std::map<std::string, float*> taps;
   int64_t launches = 0;
@@ -442,13 +492,23 @@ int conv_same(Ctx& c, const Act& in, const ConvW& w, int k, const Act& out, int 
   return c.gemm(p, EPI_PLAIN, k == 3 ? PC_CONV3 : PC_CONV_OTHER);
 }
 
+// GroupNorm statistics span all frames of the clip: with frame sharding the 16 partial sums are all-reduced (fp64)
+int gn_allreduce(Ctx& c, int slot) {
+  dawn_unet* h = c.h;
+  if (h->sh_nranks <= 1) return 0;
+  double* st = h->STATS + 16 * slot;
+  h->launches++;
+  DAWN_NCCL_OK(g_nccl.AllReduce(st, st, 16, kNcclFloat64, kNcclSum, h->sh_comm, c.st));
+  return 0;
+}
+
 // ResnetBlock_ca_mul (U:363-479)
 int resblock(Ctx& c, const ResBlockW& r, const Act& x, const Act& out) {
   dawn_unet* h = c.h;
   const int F = h->F, M = F * x.H * x.W, P = x.H * x.W;
   DAWN_CHECK(x.C == r.ci && out.C == r.co, "resblock channel mismatch: " + r.name);
   Act y{h->Y, r.co, r.co, x.H, x.W}, a1{h->A1, r.co, r.co, x.H, x.W};
-  const double count = (double)M * (r.co / 8);
+  const double count = (double)h->sh_Fglobal * P * (r.co / 8);     // GroupNorm statistics span the WHOLE clip (U:230)
   if (r.cond) {
     // cross-attention gates from the raw block input (U:454-463): LayerNorm_img folded into the q projection
     {
@@ -463,6 +523,7 @@ int resblock(Ctx& c, const ResBlockW& r, const Act& x, const Act& out) {
     DAWN_TRY(launch_ca_rstd(h->GATES, r.G, M, P, h->WT, c.st));
   }
   DAWN_TRY(conv_same(c, x, r.c1, 3, y, r.st1));
+  DAWN_TRY(gn_allreduce(c, r.st1));
   if (r.cond) {
     // a1 = SiLU(FiLM(GN(y))) + h_cond, h_cond = Wt (M x 32) @ T_f (32 x co) per frame
     Act wt{h->WT, 32, 32, x.H, x.W};
@@ -479,6 +540,7 @@ int resblock(Ctx& c, const ResBlockW& r, const Act& x, const Act& out) {
                              nullptr, 0, a1.p, a1.ld, c.st));
   }
   DAWN_TRY(conv_same(c, a1, r.c2, 3, y, r.st2));
+  DAWN_TRY(gn_allreduce(c, r.st2));
   const float* res = x.p; int ldr = x.ld;
   if (r.res) {
     GemmParams p; base_params(p, x, F);
@@ -504,39 +566,62 @@ inline int seq_block(int P) { for (int b = 16; b > 1; --b) if (P % b == 0) retur
 // TLB/latency-bound; the QKV GEMM gathers its A rows through the permutation and the out-projection scatters back.
 int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const std::string& name) {
   dawn_unet* h = c.h;
-  const int F = h->F, P = x.H * x.W, M = F * P;
+  const int F = h->F, P = x.H * x.W;
   const int pb = seq_block(P);
-  {
-    ProfScope ps(c, PC_ROWSTATS, 0, 4.0 * M * x.C);
-    DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
+  const int hl = h->sh_halo_l, hr = h->sh_halo_r, Fe = hl + F + hr;       // frames incl. neighbours' halos
+  const int Me = Fe * P;
+  Act xe = x;                                                             // the layer input over Fe frames
+  if (h->sh_nranks > 1) {
+    // exact frame sharding: the +-win_width neighbour frames of the layer input come from the adjacent ranks;
+    // K/V of those frames are re-projected locally.  Own frames are packed densely, boundaries go by NCCL send/recv.
+    const size_t rowb = (size_t)x.C * sizeof(float);
+    float* mid = h->XE + (size_t)hl * P * x.C;
+    h->launches++;
+    DAWN_CUDA_OK(cudaMemcpy2DAsync(mid, rowb, x.p, (size_t)x.ld * sizeof(float), rowb, (size_t)F * P, cudaMemcpyDeviceToDevice, c.st));
+    const size_t hcount = (size_t)h->cfg.win_width * P * x.C;
+    DAWN_NCCL_OK(g_nccl.GroupStart());
+    if (h->sh_rank > 0) {
+      DAWN_NCCL_OK(g_nccl.Send(mid, hcount, kNcclFloat32, h->sh_rank - 1, h->sh_comm, c.st));
+      DAWN_NCCL_OK(g_nccl.Recv(h->XE, hcount, kNcclFloat32, h->sh_rank - 1, h->sh_comm, c.st));
+    }
+    if (h->sh_rank < h->sh_nranks - 1) {
+      DAWN_NCCL_OK(g_nccl.Send(mid + (size_t)(F - h->cfg.win_width) * P * x.C, hcount, kNcclFloat32, h->sh_rank + 1, h->sh_comm, c.st));
+      DAWN_NCCL_OK(g_nccl.Recv(mid + (size_t)F * P * x.C, hcount, kNcclFloat32, h->sh_rank + 1, h->sh_comm, c.st));
+    }
+    DAWN_NCCL_OK(g_nccl.GroupEnd());
+    xe = Act{h->XE, x.C, x.C, x.H, x.W};
   }
   {
-    GemmParams p; base_params(p, x, F);
+    ProfScope ps(c, PC_ROWSTATS, 0, 4.0 * Me * x.C);
+    DAWN_TRY(launch_rowstats(xe.p, xe.ld, xe.C, Me, 1e-5f, h->ROWSTATS, c.st));
+  }
+  {
+    GemmParams p; base_params(p, xe, Fe);
     p.B = w.Wqkv; p.Bimg = w.Wqkv_img; p.tc_scale = 1.0f / (kTcActScale * w.Wqkv_scale); p.ldb = 768; p.N = 768; p.K = x.C;
     p.rowstats = h->ROWSTATS; p.wsum = w.wsum; p.rot = h->ROT;
     p.Out = h->QKV; p.ldo = 768;
-    p.perm_pb = pb; p.perm_F = F; p.perm_in = 1; p.perm_out = 0;
+    p.perm_pb = pb; p.perm_F = Fe; p.perm_in = 1; p.perm_out = 0;
     // output rows are written in plain order m (the permuted enumeration): treat the output as one M x 1 "image"
-    p.OH = M; p.OW = 1; p.OHs = M; p.OWs = 1; p.IH = M; p.IW = 1;
+    p.OH = Me; p.OW = 1; p.OHs = Me; p.OWs = 1; p.IH = Me; p.IW = 1;
     DAWN_TRY(c.gemm(p, EPI_QKV_TEMPORAL, PC_QKV));
   }
   {
     AttnArgs a{};
     a.qkv = h->QKV; a.ld = 768; a.out = h->O; a.ldo = 256;
-    a.nseq = P; a.L = F; a.seq_base_stride = 1; a.elem_stride = P; a.pb = pb;
-    a.band = h->cfg.win_width; a.bias = h->rel_bias; a.q_lo = 0; a.q_hi = F;
+    a.nseq = P; a.L = Fe; a.seq_base_stride = 1; a.elem_stride = P; a.pb = pb;
+    a.band = h->cfg.win_width; a.bias = h->rel_bias; a.q_lo = hl; a.q_hi = hl + F;
     double pairs = 0;
-    for (int i = 0; i < F; ++i) pairs += std::min(F - 1, i + a.band) - std::max(0, i - a.band) + 1;
-    ProfScope ps(c, PC_ATTN_CORE, 4.0 * 32 * 8 * P * pairs, 4.0 * M * 1024);
+    for (int i = hl; i < hl + F; ++i) pairs += std::min(Fe - 1, i + a.band) - std::max(0, i - a.band) + 1;
+    ProfScope ps(c, PC_ATTN_CORE, 4.0 * 32 * 8 * P * pairs, 4.0 * Me * 1024);
     if (h->use_attn_tc && attention_tc_supported(a)) DAWN_TRY(launch_attention_tc(a, c.st));
     else DAWN_TRY(launch_attention(a, c.st));
   }
   {
-    Act o{h->O, 256, 256, M, 1};
+    Act o{h->O, 256, 256, Me, 1};
     GemmParams p; base_params(p, o, 1);
     set_weights(p, w.out);
     p.P = P;
-    p.perm_pb = pb; p.perm_F = F; p.perm_in = 0; p.perm_out = 1;
+    p.perm_pb = pb; p.perm_F = Fe; p.perm_in = 0; p.perm_out = 1; p.perm_f_lo = hl; p.perm_f_hi = hl + F;
     p.Res = x.p; p.ldr = x.ld; p.Out = dst.p; p.ldo = dst.ld;
     DAWN_TRY(c.gemm(p, EPI_PLAIN, PC_OUTPROJ));
   }
@@ -784,6 +869,7 @@ int dawn_unet_create(const dawn_unet_cfg* cfg, dawn_unet** out) {
 void dawn_unet_destroy(dawn_unet* h) {
   if (!h) return;
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  if (h->sh_comm && g_nccl.ok) g_nccl.CommDestroy(h->sh_comm);
   free_all(h->owned);
   free_all(h->ws_owned);
   delete h;
@@ -906,15 +992,17 @@ int dawn_unet_set_num_frames(dawn_unet* h, int F, int height, int width) {
   max_mc = std::max(max_mc, M0 * dim);
   DAWN_TRY(dev_alloc(own, max_mc, &h->Y, cnt));
   DAWN_TRY(dev_alloc(own, max_mc, &h->A1, cnt));
-  DAWN_TRY(dev_alloc(own, M0 * 768, &h->QKV, cnt));
-  DAWN_TRY(dev_alloc(own, M0 * 256, &h->O, cnt));
-  DAWN_TRY(dev_alloc(own, M0 * 2, &h->ROWSTATS, cnt));
+  const size_t Mext = (size_t)(F + 2 * h->cfg.win_width) * P0;      // rows incl. temporal halos of a sharded clip
+  DAWN_TRY(dev_alloc(own, Mext * 768, &h->QKV, cnt));
+  DAWN_TRY(dev_alloc(own, Mext * 256, &h->O, cnt));
+  DAWN_TRY(dev_alloc(own, Mext * 2, &h->ROWSTATS, cnt));
+  DAWN_TRY(dev_alloc(own, Mext * dim, &h->XE, cnt));
   DAWN_TRY(dev_alloc(own, M0 * 24, &h->GATES, cnt));
   DAWN_TRY(dev_alloc(own, M0 * 32, &h->WT, cnt));
   DAWN_TRY(dev_alloc(own, max_bf, &h->BF, cnt));
   DAWN_TRY(dev_alloc(own, M0 * dim, &h->HF, cnt));
   DAWN_TRY(dev_alloc(own, M0 * dim, &h->HO, cnt));
-  DAWN_TRY(dev_alloc(own, (size_t)F * 32, &h->ROT, cnt));
+  DAWN_TRY(dev_alloc(own, (size_t)(F + 2 * h->cfg.win_width) * 32, &h->ROT, cnt));
   DAWN_TRY(dev_alloc(own, h->tdim, &h->TSILU, cnt));
   DAWN_TRY(dev_alloc(own, (size_t)F * 2048, &h->CTX, cnt));
   DAWN_TRY(dev_alloc(own, (size_t)F * 128, &h->KV, cnt));
@@ -944,6 +1032,7 @@ int dawn_unet_set_num_frames(dawn_unet* h, int F, int height, int width) {
     DAWN_CUDA_OK(cudaMemcpy(d, descs.data(), descs.size() * sizeof(FilmDesc), cudaMemcpyHostToDevice));
     h->film_descs = (FilmDesc*)d; h->n_film = (int)descs.size();
   }
+  h->sh_nranks = 1; h->sh_rank = 0; h->sh_Fglobal = F; h->sh_halo_l = 0; h->sh_halo_r = 0;   // a new geometry is unsharded until init_shard
   DAWN_TRY(launch_rotary_table(h->rot_freqs, F, 0, h->ROT, 0));
   DAWN_CUDA_OK(cudaDeviceSynchronize());
   return 0;
@@ -1054,6 +1143,38 @@ int dawn_unet_tap_shape(dawn_unet* h, const char* name, int* C, int* hl, int* wl
 int dawn_unet_set_tap(dawn_unet* h, const char* name, float* dst) {
   DAWN_CHECK(h && name, "null argument");
   if (dst) h->taps[name] = dst; else h->taps.erase(name);
+  return 0;
+}
+
+int dawn_nccl_unique_id(char* out128) {
+  DAWN_CHECK(out128, "null argument");
+  DAWN_TRY(load_nccl());
+  NcclUniqueId id;
+  DAWN_NCCL_OK(g_nccl.GetUniqueId(&id));
+  memcpy(out128, id.internal, 128);
+  return 0;
+}
+
+int dawn_unet_init_shard(dawn_unet* h, const char* id128, int nranks, int rank, int F_global) {
+  DAWN_CHECK(h && id128, "null argument");
+  DAWN_CHECK(h->F > 0, "set_num_frames (with the LOCAL frame count) must precede init_shard");
+  DAWN_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank");
+  DAWN_CHECK(F_global == h->F * nranks, "F_global must equal nranks * local frames (equal contiguous frame ranges)");
+  DAWN_CHECK(nranks == 1 || h->F >= h->cfg.win_width, "each rank must own at least win_width frames (only neighbours exchange halos)");
+  if (nranks > 1) {
+    DAWN_TRY(load_nccl());
+    if (h->sh_comm) { g_nccl.CommDestroy(h->sh_comm); h->sh_comm = nullptr; }
+    NcclUniqueId id;
+    memcpy(id.internal, id128, 128);
+    DAWN_NCCL_OK(g_nccl.CommInitRank(&h->sh_comm, nranks, id, rank));
+  }
+  h->sh_nranks = nranks; h->sh_rank = rank; h->sh_Fglobal = F_global;
+  h->sh_halo_l = (rank > 0) ? h->cfg.win_width : 0;
+  h->sh_halo_r = (rank < nranks - 1) ? h->cfg.win_width : 0;
+  // rotary positions of the halo-extended local sequence are GLOBAL frame indices
+  const int pos0 = rank * h->F - h->sh_halo_l;
+  DAWN_TRY(launch_rotary_table(h->rot_freqs, h->sh_halo_l + h->F + h->sh_halo_r, pos0, h->ROT, 0));
+  DAWN_CUDA_OK(cudaDeviceSynchronize());
   return 0;
 }
 

@@ -337,6 +337,21 @@ class Unet3D(nn.Module):
                                                     ctypes.c_void_p(self._cond.data_ptr()), self._stream()),
                   "dawn_unet_set_clip_invariants")
 
+    def init_shard(self, F_local, h, w, device):
+        """Exact frame sharding over the default torch.distributed group: this rank owns global frames
+        [rank*F_local, (rank+1)*F_local).  Creates the library's own NCCL communicator (unique id broadcast through
+        torch.distributed) and switches the handle to sharded mode for this geometry."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        self._ensure(device, F_local, h, w)
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            check(lib.dawn_nccl_unique_id(buf), "dawn_nccl_unique_id")
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=0)
+        with torch.cuda.device(device):
+            check(lib.dawn_unet_init_shard(self._handle, box[0], world, rank, F_local * world), "dawn_unet_init_shard")
+
     def forward_x3(self, x_t, time, out=None):
         """x_t (3, F, h, w) of the clip whose invariants were set; time int64 tensor (1,) on the device."""
         _, F, h, w = x_t.shape

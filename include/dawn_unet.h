@@ -54,9 +54,16 @@ int dawn_unet_set_param(dawn_unet* h, const char* name, const float* host, const
 int dawn_unet_commit_params(dawn_unet* h);
 
 /* replaces DynamicNfUnet3D.update_num_frames (reference :964-965) and fixes the latent size.
- * frame_lo/frame_hi select the frames this GPU owns when a clip is sharded by frame window across ranks
- * (0, F for a whole clip); halo frames for temporal attention are exchanged by the caller. */
+ * For a frame-sharded clip F is the LOCAL frame count of this rank. */
 int dawn_unet_set_num_frames(dawn_unet* h, int F, int height, int width);
+
+/* Exact frame sharding of ONE clip over `nranks` GPUs (no reference counterpart): rank r owns the contiguous
+ * global frames [r*F, (r+1)*F).  Every temporal attention exchanges its +-win_width boundary frames with the adjacent
+ * ranks (ncclSend/ncclRecv) and every GroupNorm all-reduces its 16 partial sums (fp64), so the sharded forward equals the
+ * single-GPU forward.  dawn_nccl_unique_id: call on one rank, broadcast the 128 bytes, then init_shard on every rank
+ * (after set_num_frames with the local F).  All inputs/outputs of forward* are then the LOCAL frames. */
+int dawn_nccl_unique_id(char* out128);
+int dawn_unet_init_shard(dawn_unet* h, const char* id128, int nranks, int rank, int F_global);
 
 /* Clip invariants: the 272 feature channels are identical for every frame and every
  * DDIM step (reference :1167 `fea.repeat`), and cross-attention keys/values depend only on `cond`.
