@@ -52,7 +52,9 @@ __global__ void __launch_bounds__(ATHREADS) attention_tc_kernel(AttnArgs a) {
   __half* sVl = sVh + 32 * V_LD;
   float* s_bias = reinterpret_cast<float*>(sVl + 32 * V_LD);
 
-  const int seq = blockIdx.x, head = blockIdx.y;
+  // heads are the fastest grid dimension: the 8 CTAs of one pixel run together and sweep whole 3 KB q|k|v rows
+  // (one 128-byte line per row per CTA otherwise -> one DRAM row activation per line)
+  const int head = blockIdx.x, seq = blockIdx.y;
   const int q0 = a.q_lo + blockIdx.z * QSPAN;
   const int q1 = min(q0 + QSPAN, a.q_hi);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -192,14 +194,14 @@ __global__ void __launch_bounds__(ATHREADS) attention_tc_kernel(AttnArgs a) {
           mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 1));
           mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 2));
         }
-        const float corr0 = expf(mrow[b][0] - mnew[0]), corr1 = expf(mrow[b][1] - mnew[1]);
+        const float corr0 = __expf(mrow[b][0] - mnew[0]), corr1 = __expf(mrow[b][1] - mnew[1]);
         mrow[b][0] = mnew[0]; mrow[b][1] = mnew[1];
         float psum0 = 0.f, psum1 = 0.f;
 #pragma unroll
         for (int n = 0; n < 4; ++n)
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const float pv = ok[n][c] ? expf(s[n][c] - mnew[c >> 1]) : 0.f;
+            const float pv = ok[n][c] ? __expf(s[n][c] - mnew[c >> 1]) : 0.f;
             s[n][c] = pv;
             if (c & 2) psum1 += pv; else psum0 += pv;
           }
@@ -276,7 +278,7 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
     DAWN_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr = true;
   }
-  dim3 grid(a.nseq, 8, (a.q_hi - a.q_lo + QSPAN - 1) / QSPAN);
+  dim3 grid(8, a.nseq, (a.q_hi - a.q_lo + QSPAN - 1) / QSPAN);
   attention_tc_kernel<<<grid, ATHREADS, SMEM, st>>>(a);
   DAWN_LAUNCH_OK();
   return 0;
