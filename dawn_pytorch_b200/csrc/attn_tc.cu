@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(ATHREADS) attention_tc_kernel(AttnArgs a) {
     const int nk = min(kstep, khi_all - kc0);                      // key rows of this chunk (multiple of 16 when banded)
     __syncthreads();
     // ---- stage K (row-major) and V (transposed), split into fp16 hi/lo; global loads issued in batches of 7
-    constexpr int ITEMS = KROWS * 16, BATCH = 7;
+    constexpr int ITEMS = KROWS * 16, BATCH = 14;      // every load of the chunk in flight at once (ncu: staging was latency-bound)
     static_assert(ITEMS % (ATHREADS * BATCH) == 0, "staging loop assumes full batches");
     for (int it0 = 0; it0 < ITEMS; it0 += ATHREADS * BATCH) {
       float4 vb[BATCH];

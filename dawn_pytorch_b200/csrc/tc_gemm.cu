@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t a_full[STAGES], b_full[STAGES], slot_free[STAGES], acc_full[2], acc_free[2];
   __shared__ uint32_t s_tmem_base;
-  __shared__ RowInfo s_rows[2][BM];
+  __shared__ RowInfo s_rows[4][BM];
   __shared__ float s_stat[NWG][16];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -176,14 +176,20 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
 
   if (warp < 8) {
     // =============================================================== A producers
+    // Work items are (tile, k-panel) pairs flattened over this CTA's tiles, so the register prefetch keeps running
+    // across tile boundaries (with K = 64 a tile is a single panel: per-tile prologues exposed the full load latency).
     const int c16 = tid & 7;            // 16-byte chunk inside the 128-byte row
     const int r0 = tid >> 3;            // rows r0 + 32 q, q = 0..3
+    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_items = my_tiles * KC;
+    int last_table = -1;
     uint32_t it = 0;
-    int tile_iter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+
+    // row table of this CTA's T-th tile (ring of 4: prefetch runs at most 2 items = 2 tiles ahead of the stores)
+    auto ensure_table = [&](int T) {
+      if (T <= last_table) return;
+      const int tile = blockIdx.x + T * gridDim.x;
       const int m0 = (tile / tiles_n) * BM;
-      RowInfo* rows = s_rows[tile_iter & 1];
-      // row table for this tile (double-buffered across tiles; synchronised among the producers only)
       if (tid < BM) {
         const int m = m0 + tid;
         RowInfo ri;
@@ -196,84 +202,87 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
         } else {
           ri.pix = -1; ri.iy = 0; ri.ix = 0;
         }
-        rows[tid] = ri;
+        s_rows[T & 3][tid] = ri;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-
-      auto load_panel = [&](float4 (&v)[8], int kc) {
-        const int tap = kc / chunks_per_tap;
-        const int c0 = (kc - tap * chunks_per_tap) * BKP;
-        const int dy = p.dy[tap], dx = p.dx[tap];
+      last_table = T;
+    };
+    auto load_item = [&](float4 (&v)[8], int g) {
+      const int T = g / KC, kc = g - T * KC;
+      ensure_table(T);
+      const RowInfo* rows = s_rows[T & 3];
+      const int tap = kc / chunks_per_tap;
+      const int c0 = (kc - tap * chunks_per_tap) * BKP;
+      const int dy = p.dy[tap], dx = p.dx[tap];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const RowInfo ri = rows[r0 + 32 * q];
-          const int iy = ri.iy + dy, ix = ri.ix + dx;
-          const bool ok = (ri.pix >= 0) && (iy >= 0) && (iy < p.IH) && (ix >= 0) && (ix < p.IW);
-          if (ok) {
-            const float4* src = reinterpret_cast<const float4*>(p.A + (size_t)(ri.pix + iy * p.IW + ix) * p.lda + c0) + 2 * c16;
-            v[2 * q] = __ldg(src);
-            v[2 * q + 1] = __ldg(src + 1);
-          } else {
-            v[2 * q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            v[2 * q + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+      for (int q = 0; q < 4; ++q) {
+        const RowInfo ri = rows[r0 + 32 * q];
+        const int iy = ri.iy + dy, ix = ri.ix + dx;
+        const bool ok = (ri.pix >= 0) && (iy >= 0) && (iy < p.IH) && (ix >= 0) && (ix < p.IW);
+        if (ok) {
+          const float4* src = reinterpret_cast<const float4*>(p.A + (size_t)(ri.pix + iy * p.IW + ix) * p.lda + c0) + 2 * c16;
+          v[2 * q] = __ldg(src);
+          v[2 * q + 1] = __ldg(src + 1);
+        } else {
+          v[2 * q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          v[2 * q + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-      };
-      auto store_panel = [&](const float4 (&v)[8]) {
-        const int s = it % STAGES;
-        const uint32_t round = it / STAGES;
-        const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && tid == 0;
-        long long t0 = 0;
-        if (tr) t0 = clock64();
-        mbar_wait(&slot_free[s], (round & 1) ^ 1);
-        if (tr) { const long long t1 = clock64(); p.trace[6] += (unsigned long long)(t1 - t0); t0 = t1; }
-        uint8_t* a_hi = smem + s * STAGE_BYTES;
-        uint8_t* a_lo = a_hi + A_PANEL;
+      }
+    };
+    auto store_item = [&](const float4 (&v)[8]) {
+      const int s = it % STAGES;
+      const uint32_t round = it / STAGES;
+      const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && tid == 0;
+      long long t0 = 0;
+      if (tr) t0 = clock64();
+      mbar_wait(&slot_free[s], (round & 1) ^ 1);
+      if (tr) { const long long t1 = clock64(); p.trace[6] += (unsigned long long)(t1 - t0); t0 = t1; }
+      uint8_t* a_hi = smem + s * STAGE_BYTES;
+      uint8_t* a_lo = a_hi + A_PANEL;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t h[4], l[4];
-          split_f16x2(v[2 * q].x, v[2 * q].y, h[0], l[0]);
-          split_f16x2(v[2 * q].z, v[2 * q].w, h[1], l[1]);
-          split_f16x2(v[2 * q + 1].x, v[2 * q + 1].y, h[2], l[2]);
-          split_f16x2(v[2 * q + 1].z, v[2 * q + 1].w, h[3], l[3]);
-          const uint32_t off = swz(r0 + 32 * q, c16);
-          *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
-        }
-        fence_proxy_async();
-        mbar_arrive(&a_full[s]);
-        if (tr) p.trace[7] += (unsigned long long)(clock64() - t0);
-        ++it;
-      };
+      for (int q = 0; q < 4; ++q) {
+        uint32_t h[4], l[4];
+        split_f16x2(v[2 * q].x, v[2 * q].y, h[0], l[0]);
+        split_f16x2(v[2 * q].z, v[2 * q].w, h[1], l[1]);
+        split_f16x2(v[2 * q + 1].x, v[2 * q + 1].y, h[2], l[2]);
+        split_f16x2(v[2 * q + 1].z, v[2 * q + 1].w, h[3], l[3]);
+        const uint32_t off = swz(r0 + 32 * q, c16);
+        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(&a_full[s]);
+      if (tr) p.trace[7] += (unsigned long long)(clock64() - t0);
+      ++it;
+    };
 
-      // global loads run ahead of the split/store in statically indexed register buffers:
-      // two panels ahead (3 buffers) for BN = 64, one panel ahead (2 buffers) for BN = 128 (96-register budget)
-      if constexpr (BN == 64) {
-        float4 v0[8], v1[8], v2[8];
-        load_panel(v0, 0);
-        if (KC > 1) load_panel(v1, 1);
-        for (int kc = 0; kc < KC; kc += 3) {
-          if (kc + 2 < KC) load_panel(v2, kc + 2);
-          store_panel(v0);
-          if (kc + 1 < KC) {
-            if (kc + 3 < KC) load_panel(v0, kc + 3);
-            store_panel(v1);
-          }
-          if (kc + 2 < KC) {
-            if (kc + 4 < KC) load_panel(v1, kc + 4);
-            store_panel(v2);
-          }
+    // global loads run ahead of the split/store in statically indexed register buffers:
+    // two items ahead (3 buffers) for BN = 64, one item ahead (2 buffers) for BN = 128 (96-register budget)
+    if constexpr (BN == 64) {
+      float4 v0[8], v1[8], v2[8];
+      if (n_items > 0) load_item(v0, 0);
+      if (n_items > 1) load_item(v1, 1);
+      for (int g = 0; g < n_items; g += 3) {
+        if (g + 2 < n_items) load_item(v2, g + 2);
+        store_item(v0);
+        if (g + 1 < n_items) {
+          if (g + 3 < n_items) load_item(v0, g + 3);
+          store_item(v1);
         }
-      } else {
-        float4 v0[8], v1[8];
-        load_panel(v0, 0);
-        for (int kc = 0; kc < KC; kc += 2) {
-          if (kc + 1 < KC) load_panel(v1, kc + 1);
-          store_panel(v0);
-          if (kc + 1 < KC) {
-            if (kc + 2 < KC) load_panel(v0, kc + 2);
-            store_panel(v1);
-          }
+        if (g + 2 < n_items) {
+          if (g + 4 < n_items) load_item(v1, g + 4);
+          store_item(v2);
+        }
+      }
+    } else {
+      float4 v0[8], v1[8];
+      if (n_items > 0) load_item(v0, 0);
+      for (int g = 0; g < n_items; g += 2) {
+        if (g + 1 < n_items) load_item(v1, g + 1);
+        store_item(v0);
+        if (g + 1 < n_items) {
+          if (g + 2 < n_items) load_item(v0, g + 2);
+          store_item(v1);
         }
       }
     }
