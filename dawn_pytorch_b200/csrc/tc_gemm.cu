@@ -40,7 +40,8 @@ struct Cfg {
   static constexpr int MMA_WARP = (NPROD + 128 * NWG) / 32;
   static constexpr int LOAD_WARP = MMA_WARP + 1;
   static constexpr int TMEM_COLS = 2 * BN;                   // two accumulator buffers
-  static constexpr int SMEM_DYN = STAGES * STAGE_BYTES + 1024;
+  static constexpr int EPI_STAGE = NWG * 4 * 32 * 20 * 4;     // per epilogue warp: 32 rows x (16 + 4 pad) floats
+  static constexpr int SMEM_DYN = STAGES * STAGE_BYTES + EPI_STAGE + 1024;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -136,6 +137,35 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, ui
   const __half2 l = __floats2half2_rn(x0 - h0, x1 - h1);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// Store this warp's 32 rows x 64 columns (row-per-lane registers) to global memory with full-sector transactions:
+// 16 columns at a time go through a per-warp shared-memory buffer so that one store instruction writes 8 rows x 64
+// contiguous bytes instead of 32 rows x 16 bytes at a multi-KB stride (measured: the strided form capped the qkv
+// projection's output stream at ~1.6 TB/s).
+__device__ __forceinline__ void store_rows_coalesced(float* wbuf, const float (&acc)[64], float* out, size_t opix, int ldo,
+                                                     int n0, bool rv, int lane) {
+  const uint32_t op_lo = (uint32_t)opix, op_hi = (uint32_t)((unsigned long long)opix >> 32);
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4*>(wbuf + lane * 20 + j * 4) =
+          make_float4(acc[pass * 16 + j * 4], acc[pass * 16 + j * 4 + 1], acc[pass * 16 + j * 4 + 2], acc[pass * 16 + j * 4 + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = (lane >> 2) + 8 * k, c4 = lane & 3;
+      const float4 v = *reinterpret_cast<const float4*>(wbuf + r * 20 + c4 * 4);
+      const uint32_t lo = __shfl_sync(0xffffffffu, op_lo, r), hi = __shfl_sync(0xffffffffu, op_hi, r);
+      const int ok = __shfl_sync(0xffffffffu, rv ? 1 : 0, r);
+      if (ok) {
+        const size_t px = ((size_t)hi << 32) | lo;
+        *reinterpret_cast<float4*>(out + px * ldo + n0 + pass * 16 + c4 * 4) = v;
+      }
+    }
+  }
 }
 
 struct RowInfo { int pix; int iy, ix; };     // per tile row: input frame base pixel, top-left input coordinate
@@ -364,6 +394,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
     float* s_st = s_stat[wg];
     const int bar_id = 2 + wg;
     constexpr int EN = 64;                                 // columns per epilogue thread
+    float* wbuf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + ((wg * 4 + ew) * 32 * 20);
     uint32_t cg = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN + wg * EN;
@@ -412,8 +443,12 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
 
       if (EPI == EPI_PLAIN) {
         if (p.bias) {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
-          for (int i = 0; i < EN; ++i) acc[i] += p.bias[n0 + i];
+          for (int i = 0; i < EN / 4; ++i) {
+            const float4 b = __ldg(bp + i);
+            acc[4 * i] += b.x; acc[4 * i + 1] += b.y; acc[4 * i + 2] += b.z; acc[4 * i + 3] += b.w;
+          }
         }
         if (rv && p.Res) {
           const float4* rp = reinterpret_cast<const float4*>(p.Res + opix * p.ldr + n0);
@@ -423,11 +458,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
             acc[4 * i] += r.x; acc[4 * i + 1] += r.y; acc[4 * i + 2] += r.z; acc[4 * i + 3] += r.w;
           }
         }
-        if (rv) {
-          float4* op = reinterpret_cast<float4*>(p.Out + opix * p.ldo + n0);
-#pragma unroll
-          for (int i = 0; i < EN / 4; ++i) op[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
-        }
+        store_rows_coalesced(wbuf, acc, p.Out, opix, p.ldo, n0, rv, lane);
         if (p.stats != nullptr) {
           // GroupNorm partial statistics (U:230): per 8-column sub-block, reduced over the warp's 32 rows
           if (etid < 16) s_st[etid] = 0.f;
@@ -505,10 +536,8 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
             const float er = expf(sr - mx), en = expf(sn - mx);
             if (rv) p.gates[(size_t)m * 24 + ca * 8 + hd] = er / (er + en);
           }
-        } else if (rv) {
-          float4* op = reinterpret_cast<float4*>(p.Out + opix * p.ldo + n0);
-#pragma unroll
-          for (int i = 0; i < EN / 4; ++i) op[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+        } else {
+          store_rows_coalesced(wbuf, acc, p.Out, opix, p.ldo, n0, rv, lane);
         }
       }
       if (tr_e) p.trace[10] += (unsigned long long)(clock64() - te0);

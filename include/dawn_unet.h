@@ -103,6 +103,13 @@ int64_t dawn_unet_last_launch_count(dawn_unet* h);
 /* bytes of device workspace currently held */
 int64_t dawn_unet_workspace_bytes(dawn_unet* h);
 
+/* One DDIM update around the UNet (reference GaussianDiffusion.ddim_sample :1169-1205), in place on x (device, n floats):
+ *   x0 = ca*x - cb*eps;  s = max(1, quantile_q(|x0|)) over all n values (torch.quantile semantics) if q > 0, else 1;
+ *   x = clamp(x0,-s,s)/s * sqrt_an + c*eps + sigma*noise      (noise = NULL for the last step)
+ * scratch: device buffer of n + 512 32-bit words.  No host synchronisation. */
+int dawn_ddim_step(float* x, const float* eps, const float* noise, int64_t n, float ca, float cb, float sqrt_an, float c,
+                   float sigma, float q, void* scratch, void* stream);
+
 /* self-test of the tcgen05 contraction kernel against the mma.sync kernel on a random k x k convolution
  * (F frames of H x W, Cin -> N channels); reports max |difference| (outputs and, if requested, GroupNorm sums). */
 int dawn_selftest_tc_gemm(int F, int H, int W, int Cin, int N, int ksize, int with_stats, float* max_abs_diff, float* max_abs_ref);

@@ -137,3 +137,32 @@ def test_full_size_properties_cfg3():
     d_near = (c[:, 0] - a[:, 0]).abs().max().item()
     d_far = (c[:, 199] - a[:, 199]).abs().max().item()
     assert d_near > 1e-2 and d_far < d_near
+
+
+def test_ddim_sampler_steps_match_reference_golden():
+    """Row a16: DDIM update (x0, exact clip-wide 0.9-quantile threshold, eta-noise) around the CUDA UNet, against the
+    reference's own arithmetic with injected noise (tests/golden/ddim_odd.npz: steps 952->904, 523->476, 47->0)."""
+    from dawn_pytorch_b200 import DynamicNfGaussianDiffusion
+    net = G.cuda_net()
+    D = DynamicNfGaussianDiffusion(denoise_fn=net, num_frames=40, image_size=32, sampling_timesteps=20, timesteps=1000,
+                                   loss_type='l2', use_dynamic_thres=True, null_cond_prob=0.1, ddim_sampling_eta=1.0).cuda()
+    assert len(D.state_dict()) == 912                      # 900 UNet entries + 12 schedule buffers (SURVEY App. B)
+    g = np.load(__import__("os").path.join(G.ROOT, "tests", "golden", "ddim_odd.npz"))
+    F, h, w, _ = G.CASES["odd"]
+    x_t, fea, cond = W.synth_inputs("odd", F, h, w)
+    steps = [tuple(int(v) for v in p) for p in g["steps"].tolist()]
+    assert steps[0] == D.ddim_schedule()[0] and steps[-1] == D.ddim_schedule()[-1]
+    D.update_num_frames(F)
+
+    def noise_fn(k, shape):
+        if k < 0:
+            return x_t.clone()
+        return torch.from_numpy(W.pseudo_normal(f"odd/noise{k}", (1,) + tuple(shape)))[0]
+
+    for nsteps in (1, 3):
+        img = D.ddim_sample(fea.cuda(), (1, 3, F, h, w), cond=cond.cuda(), noise_fn=noise_fn, pairs=steps[:nsteps])
+        torch.cuda.synchronize()
+        ref = torch.from_numpy(g["x_after"][nsteps - 1])
+        d = (img.cpu() - ref).abs().max().item()
+        print(f"ddim {nsteps} step(s): max|d| = {d:.3e}")
+        assert d < 2e-4
