@@ -5,7 +5,10 @@
 
 A "step" is one UNet forward (`forward_with_cond_scale`, cond_scale=1) over a whole synthetic clip:
 BASELINE configs[2] = 200 frames of a 64x64 latent (256x256 video), windowed temporal attention.
-N > 1 (torchrun, one rank per GPU): every rank denoises its own 200-frame clip ("replicas", weak scaling).
+N > 1 (torchrun, one rank per GPU): ONE clip of 200*N frames is sharded by contiguous frame range, 200 frames per
+GPU (weak scaling), exactly: +-40-frame halo exchange before each of the 10 temporal attentions (ncclSend/Recv) and a
+16-double all-reduce per GroupNorm (40 per step) inside the library; `value` counts 200-frame-clip equivalents
+(frames denoised per second / 200).  `--replicas` runs one independent 200-frame clip per GPU instead.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -155,6 +158,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: independent clips per GPU instead of one frame-sharded clip")
     ap.add_argument("--cpu-baseline-worker", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -167,7 +171,11 @@ def main():
     net = DynamicNfUnet3D(**CTOR).eval()          # random-init weights of the reference architecture
     sd_cpu = {k: v.detach().clone() for k, v in net.state_dict().items()}
     config = {"workload": "configs[2]: 256x256 video = 64x64 latent, 200 frames, windowed (+-40) temporal attention, 1 UNet forward per step",
-              "frames": F_CLIP, "latent": [H_LAT, W_LAT], "parallelism": f"replicas x{args.gpus} (one 200-frame clip per GPU)" if args.gpus > 1 else "single GPU",
+              "frames": F_CLIP * (1 if (args.gpus == 1 or args.replicas) else args.gpus), "latent": [H_LAT, W_LAT],
+              "parallelism": ("single GPU" if args.gpus == 1 else
+                              f"replicas x{args.gpus} (one 200-frame clip per GPU, no collective)" if args.replicas else
+                              f"exact frame sharding x{args.gpus}: one {F_CLIP * args.gpus}-frame clip, {F_CLIP} frames/GPU; per step 10 halo "
+                              "exchanges (ncclSend/Recv of 40 boundary frames) + 40 GroupNorm all-reduces (16 fp64) over NVLink"),
               "l2": "per-step working set ~7 GB >> 126 MB L2 (inputs larger than L2, no explicit flush)"}
 
     if args.cpu_baseline_worker:
@@ -196,8 +204,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     net = net.to(dev)
+    sharded = world > 1 and not args.replicas
     x_t, fea, cond = synth_clip(1 + rank)
+    if sharded:                                   # every rank needs the same per-clip features; frames differ per rank
+        fea = synth_clip(1)[1]
     net.update_num_frames(F_CLIP)
+    if sharded:
+        net.init_shard(F_CLIP, H_LAT, W_LAT, dev)
     xt_d, fea_d, cond_d = x_t.to(dev), fea.to(dev), cond.to(dev)
     t_d = torch.full((1,), 500, dtype=torch.long, device=dev)
     out_d = torch.empty((3, F_CLIP, H_LAT, W_LAT), device=dev)
