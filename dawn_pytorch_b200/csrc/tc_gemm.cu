@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
     const int n_items = my_tiles * KC;
     int last_table = -1;
     uint32_t it = 0;
+    long long tp_wait = 0, tp_work = 0, tp_load = 0;       // trace accumulators (registers; written once at the end)
 
     // row table of this CTA's T-th tile (ring of 4: prefetch runs at most 2 items = 2 tiles ahead of the stores)
     auto ensure_table = [&](int T) {
@@ -238,6 +239,8 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
       last_table = T;
     };
     auto load_item = [&](float4 (&v)[8], int g) {
+      const bool trl = (p.trace != nullptr) && blockIdx.x == 0 && tid == 0;
+      const long long tl0 = trl ? clock64() : 0;
       const int T = g / KC, kc = g - T * KC;
       ensure_table(T);
       const RowInfo* rows = s_rows[T & 3];
@@ -258,6 +261,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
           v[2 * q + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      if (trl) tp_load += clock64() - tl0;
     };
     auto store_item = [&](const float4 (&v)[8]) {
       const int s = it % STAGES;
@@ -316,10 +320,14 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
         }
       }
     }
+    if (p.trace != nullptr && blockIdx.x == 0 && tid == 0) {
+      p.trace[6] = (unsigned long long)tp_wait; p.trace[7] = (unsigned long long)tp_work; p.trace[11] = (unsigned long long)tp_load;
+    }
   } else if (warp == LOAD_WARP) {
     // =============================================================== weight loader (pre-swizzled hi|lo images)
     if (lane == 0) {
       uint32_t it = 0;
+      long long tl_wait = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % tiles_n;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(Bimg) + (size_t)nt * KC * (2 * B_PANEL);
@@ -330,11 +338,12 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
           long long t0 = 0;
           if (tr) t0 = clock64();
           mbar_wait(&slot_free[s], (round & 1) ^ 1);
-          if (tr) p.trace[8] += (unsigned long long)(clock64() - t0);
+          if (tr) tl_wait += clock64() - t0;
           mbar_arrive_expect_tx(&b_full[s], 2 * B_PANEL);
           bulk_copy_g2s(smem + s * STAGE_BYTES + 2 * A_PANEL, src + (size_t)kc * (2 * B_PANEL), 2 * B_PANEL, &b_full[s]);
         }
       }
+      if (p.trace != nullptr && blockIdx.x == 0) p.trace[8] = (unsigned long long)tl_wait;
     }
   } else if (warp == MMA_WARP) {
     // =============================================================== MMA issuer
@@ -396,6 +405,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
     constexpr int EN = 64;                                 // columns per epilogue thread
     float* wbuf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + ((wg * 4 + ew) * 32 * 20);
     uint32_t cg = 0;
+    long long te_wait = 0, te_final = 0, te_drain = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN + wg * EN;
       float acc[EN];
@@ -408,7 +418,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
         long long t0 = 0;
         if (tr) t0 = clock64();
         mbar_wait(&acc_full[buf], (cg >> 1) & 1);
-        if (tr) p.trace[9] += (unsigned long long)(clock64() - t0);
+        if (tr) { const long long t1 = clock64(); te_wait += t1 - t0; t0 = t1; }
         tc_fence_after();
 #pragma unroll
         for (int q = 0; q < EN / 16; ++q) {
@@ -419,6 +429,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
         }
         tc_fence_before();
         mbar_arrive(&acc_free[buf]);
+        if (tr) te_drain += clock64() - t0;
       }
 
 #pragma unroll
@@ -540,7 +551,10 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
           store_rows_coalesced(wbuf, acc, p.Out, opix, p.ldo, n0, rv, lane);
         }
       }
-      if (tr_e) p.trace[10] += (unsigned long long)(clock64() - te0);
+      if (tr_e) te_final += clock64() - te0;
+    }
+    if (p.trace != nullptr && blockIdx.x == 0 && etid == 0 && wg == 0) {
+      p.trace[9] = (unsigned long long)te_wait; p.trace[10] = (unsigned long long)te_final; p.trace[12] = (unsigned long long)te_drain;
     }
   }
 
