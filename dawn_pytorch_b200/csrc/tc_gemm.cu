@@ -291,7 +291,10 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
         *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
       }
-      fence_proxy_async();
+      // no proxy fence here: fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and would make every
+      // producer thread drain its outstanding prefetch loads once per panel (measured ~1000 cycles).  The st.shared
+      // above and this arrive retire in order through the same shared-memory pipe; the issuer thread runs the proxy
+      // fence after acquiring a_full (it has no loads in flight), before the async-proxy reads of tcgen05.mma.
       mbar_arrive_relaxed(&a_full[s]);
       if (tr) p.trace[7] += (unsigned long long)(clock64() - t0);
       ++it;
@@ -376,6 +379,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
           if (tr) { const long long t1 = clock64(); t_a += t1 - t0; t0 = t1; }
           mbar_wait(&b_full[s], round & 1);
           if (tr) { const long long t1 = clock64(); t_b += t1 - t0; t0 = t1; }
+          fence_proxy_async();          // generic-proxy operand writes of the producers -> async proxy (see store_item)
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint64_t ahi = make_desc(sa), alo = make_desc(sa + A_PANEL);
