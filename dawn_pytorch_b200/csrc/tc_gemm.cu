@@ -219,8 +219,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
     const int r0 = tid >> 3;            // rows r0 + 32 q, q = 0..3
     const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int n_items = my_tiles * KC;
-    int last_table = -1, cur_T = -1;
-    RowInfo rcur[4];
+    int last_table = -1;
     uint32_t it = 0;
     long long tp_wait = 0, tp_work = 0, tp_load = 0;       // trace accumulators (registers; written once at the end)
 
@@ -250,18 +249,14 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
       const bool trl = (p.trace != nullptr) && blockIdx.x == 0 && tid == 0;
       const long long tl0 = trl ? clock64() : 0;
       const int T = g / KC, kc = g - T * KC;
-      if (T != cur_T) {               // row coordinates live in registers; shared memory is read once per tile, not per panel
-        ensure_table(T);              // (an LDS per panel shared scoreboard slots with the in-flight prefetch loads and
-        cur_T = T;                    //  stalled the issue of every new batch by about one memory latency)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) rcur[q] = s_rows[T & 3][r0 + 32 * q];
-      }
+      ensure_table(T);
+      const RowInfo* rows = s_rows[T & 3];
       const int tap = kc / chunks_per_tap;
       const int c0 = (kc - tap * chunks_per_tap) * BKP;
       const int dy = p.dy[tap], dx = p.dx[tap];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const RowInfo ri = rcur[q];
+        const RowInfo ri = rows[r0 + 32 * q];
         const int iy = ri.iy + dy, ix = ri.ix + dx;
         const bool ok = (ri.pix >= 0) && (iy >= 0) && (iy < p.IH) && (ix >= 0) && (ix < p.IW);
         if (ok) {
