@@ -26,13 +26,14 @@ namespace {
 constexpr int BM = 128;
 constexpr int BKP = 64;                 // K elements per panel row (64 fp16 = 128 bytes)
 constexpr int CHUNK = 4;                // panels accumulated inside TMEM before a drain (K = 128)
-constexpr int A_PANEL = BM * 128;       // 16 KB
+constexpr int A_PANEL_MIN = BM * 128;    // 16 KB
 constexpr int NPROD = 256;              // producer threads (warps 0-7)
 
 // BN = 64: one epilogue warpgroup, 4 stages of 48 KB.  BN = 128: two epilogue warpgroups (64 columns each), 3 stages of 64 KB.
 template <int BN>
 struct Cfg {
   static constexpr int NWG = BN / 64;                        // epilogue warpgroups
+  static constexpr int A_PANEL = (BN == 64) ? 18 * 1024 : A_PANEL_MIN;   // BN = 64: 16 spare rows for shifted-window experiments
   static constexpr int B_PANEL = BN * 128;
   static constexpr int STAGE_BYTES = 2 * A_PANEL + 2 * B_PANEL;
   static constexpr int STAGES = (BN == 64) ? 4 : 3;
@@ -130,6 +131,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// descriptor for an operand whose first row sits `shift` rows (of 128 B) into a 1024-byte swizzle atom
+__device__ __forceinline__ uint64_t make_desc_shifted(uint32_t saddr_aligned, int shift) {
+  return make_desc(saddr_aligned + shift * 128) | ((uint64_t)(shift & 7) << 49);
+}
 // byte offset of 16-byte chunk c (0..7) of row r inside a swizzled panel
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
 
@@ -181,7 +186,7 @@ template <int EPI, int BN>
 __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const GemmParams p, const float* __restrict__ Bimg, int KC,
                                                                        int tiles_m, int tiles_n) {
   using C = Cfg<BN>;
-  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_PANEL = C::B_PANEL, TMEM_COLS = C::TMEM_COLS;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_PANEL = C::B_PANEL, TMEM_COLS = C::TMEM_COLS, A_PANEL = C::A_PANEL;
   constexpr int MMA_WARP = C::MMA_WARP, LOAD_WARP = C::LOAD_WARP, NWG = C::NWG;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t a_full[STAGES], b_full[STAGES], slot_free[STAGES], acc_full[2], acc_free[2];
@@ -220,6 +225,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
     const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int n_items = my_tiles * KC;
     int last_table = -1;
+    const int xshift = (BN == 64) ? p.exp_shift : 0;      // experiment: operand rows stored `xshift` rows down
     uint32_t it = 0;
     long long tp_wait = 0, tp_work = 0, tp_load = 0;       // trace accumulators (registers; written once at the end)
 
@@ -287,7 +293,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
         split_f16x2(v[2 * q].z, v[2 * q].w, h[1], l[1]);
         split_f16x2(v[2 * q + 1].x, v[2 * q + 1].y, h[2], l[2]);
         split_f16x2(v[2 * q + 1].z, v[2 * q + 1].w, h[3], l[3]);
-        const uint32_t off = swz(r0 + 32 * q, c16);
+        const uint32_t off = swz(r0 + 32 * q + xshift, c16);
         *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
       }
@@ -382,7 +388,8 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
           fence_proxy_async();          // generic-proxy operand writes of the producers -> async proxy (see store_item)
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-          const uint64_t ahi = make_desc(sa), alo = make_desc(sa + A_PANEL);
+          const int xs = (BN == 64) ? p.exp_shift : 0;
+          const uint64_t ahi = make_desc_shifted(sa, xs), alo = make_desc_shifted(sa + A_PANEL, xs);
           const uint64_t bhi = make_desc(sa + 2 * A_PANEL), blo = make_desc(sa + 2 * A_PANEL + B_PANEL);
           const uint32_t d = tmem_base + buf * BN;
 #pragma unroll

@@ -1286,6 +1286,7 @@ int dawn_selftest_tc_gemm(int F, int H, int W, int Cin, int N, int ksize, int wi
     if (with_stats) p.stats = (double*)dS + 16;
     p.Out = dO2;
     if (!tc_gemm_supported(p, EPI_PLAIN)) { cleanup(); set_last_error("selftest: shape not supported by tc_gemm"); return -1; }
+    if (getenv("DAWN_TC_SHIFT")) p.exp_shift = atoi(getenv("DAWN_TC_SHIFT"));
     unsigned long long* dT = nullptr;
     if (getenv("DAWN_TC_TRACE")) {
       float* t; if (dev_alloc(own, 64, &t)) { cleanup(); return -2; }
