@@ -293,7 +293,12 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
         split_f16x2(v[2 * q].z, v[2 * q].w, h[1], l[1]);
         split_f16x2(v[2 * q + 1].x, v[2 * q + 1].y, h[2], l[2]);
         split_f16x2(v[2 * q + 1].z, v[2 * q + 1].w, h[3], l[3]);
-        const uint32_t off = swz(r0 + 32 * q + xshift, c16);
+        uint32_t off;
+        {
+          const int rr = r0 + 32 * q, rs = rr + (xshift & 15);
+          const int ph = ((xshift >> 4) & 2) ? (rr & 7) : (rs & 7);         // mode bit 1: swizzle phase relative to the window start
+          off = (uint32_t)((rs >> 3) * 1024 + (rs & 7) * 128 + ((c16 ^ ph) << 4));
+        }
         *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
       }
@@ -389,7 +394,9 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const int xs = (BN == 64) ? p.exp_shift : 0;
-          const uint64_t ahi = make_desc_shifted(sa, xs), alo = make_desc_shifted(sa + A_PANEL, xs);
+          const int xsh = xs & 15, xbo = ((xs >> 4) & 1) ? 0 : xsh;              // mode bit 0: base_offset forced to 0
+          const uint64_t ahi = make_desc(sa + xsh * 128) | ((uint64_t)(xbo & 7) << 49);
+          const uint64_t alo = make_desc(sa + A_PANEL + xsh * 128) | ((uint64_t)(xbo & 7) << 49);
           const uint64_t bhi = make_desc(sa + 2 * A_PANEL), blo = make_desc(sa + 2 * A_PANEL + B_PANEL);
           const uint32_t d = tmem_base + buf * BN;
 #pragma unroll
