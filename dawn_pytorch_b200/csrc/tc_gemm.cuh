@@ -13,5 +13,8 @@ bool tc_gemm_supported(const GemmParams& p, int epi);
 size_t tc_pack_weights(const float* Bkn, int K, int N, int ldb, std::vector<float>& out, float* scale);
 constexpr float kTcActScale = 1.0f;
 int launch_tc_gemm(const GemmParams& p, const float* Bimg, int epi, cudaStream_t st);
+// halo-tile 3x3 convolution (tc_conv3.cu): same weight image, activations staged once per 64-channel chunk
+bool tc_conv3_supported(const GemmParams& p, int epi);
+int launch_tc_conv3(const GemmParams& p, const float* Bimg, cudaStream_t st);
 
 }  // namespace dawn

@@ -130,6 +130,7 @@ struct dawn_unet {
   std::unordered_map<std::string, HostParam> raw;
   bool committed = false;
   bool use_tc = true;                          // tcgen05 contraction path (DAWN_TC=0 falls back to mma.sync)
+  bool use_conv3 = true;                       // halo-tile tcgen05 3x3 conv (DAWN_TC_CONV3=0 falls back to the per-tap GEMM)
   bool use_attn_tc = true;                     // tensor-core attention core (DAWN_ATTN_TC=0 falls back to SIMT)
 
   // packed weights
@@ -477,6 +478,7 @@ int Ctx::gemm(const GemmParams& p, int epi, int cat) {
   if (p.Y) bytes += 4.0 * p.M * p.N;
   if (epi == EPI_CA_GATE) bytes = 4.0 * p.M * (p.Cin + 24.0);
   ProfScope ps(*this, cat, flops, bytes);
+  if (h->use_tc && h->use_conv3 && p.Bimg != nullptr && tc_conv3_supported(p, epi)) return launch_tc_conv3(p, p.Bimg, st);
   if (h->use_tc && p.Bimg != nullptr && tc_gemm_supported(p, epi)) return launch_tc_gemm(p, p.Bimg, epi, st);
   return launch_gemm(p, epi, st);
 }
@@ -853,6 +855,7 @@ int dawn_unet_create(const dawn_unet_cfg* cfg, dawn_unet** out) {
   h->cfg = *cfg;
   { const char* e = getenv("DAWN_TC"); h->use_tc = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_ATTN_TC"); h->use_attn_tc = !(e && e[0] == '0'); }
+  { const char* e = getenv("DAWN_TC_CONV3"); h->use_conv3 = !(e && e[0] == '0'); }
   h->nlev = cfg->n_levels;
   h->dims.push_back(cfg->dim);
   for (int i = 0; i < cfg->n_levels; ++i) h->dims.push_back(cfg->dim * cfg->dim_mults[i]);
@@ -1292,7 +1295,8 @@ int dawn_selftest_tc_gemm(int F, int H, int W, int Cin, int N, int ksize, int wi
       float* t; if (dev_alloc(own, 64, &t)) { cleanup(); return -2; }
       cudaMemset(t, 0, 256); dT = (unsigned long long*)t; p.trace = dT;
     }
-    rc = launch_tc_gemm(p, dImg, EPI_PLAIN, 0);
+    if (getenv("DAWN_SELFTEST_CONV3") && tc_conv3_supported(p, EPI_PLAIN)) { rc = launch_tc_conv3(p, dImg, 0); printf("  (halo-tile conv3 kernel)\n"); }
+    else rc = launch_tc_gemm(p, dImg, EPI_PLAIN, 0);
     if (rc == 0 && dT) {
       unsigned long long tr[16];
       cudaMemcpy(tr, dT, sizeof(tr), cudaMemcpyDeviceToHost);
