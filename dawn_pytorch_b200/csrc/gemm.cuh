@@ -41,7 +41,8 @@ struct GemmParams {
   const float* Res; int ldr;
   double* stats; int cpg;  // GroupNorm accumulators [groups][2], channels per group
   // LayerNorm fold
-  const float* rowstats;   // [M][2] (mu, rstd)
+  const float* rowstats;   // [M][2] (mu, rstd); null on the tcgen05 path when ln_inline is set
+  int ln_inline;           // tcgen05 1x1 GEMMs: the producers accumulate each row's sum / sum of squares while they stream it
   const float* wsum;       // [N]  sum_k B[k][n]
   const float* rot;        // [F][16][2] (cos, sin)
   int P;                   // positions per frame (row -> frame index)

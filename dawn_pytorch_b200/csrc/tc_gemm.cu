@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t a_full[STAGES], b_full[STAGES], slot_free[STAGES], acc_full[2], acc_free[2];
   __shared__ uint32_t s_tmem_base;
-  __shared__ RowInfo s_rows[4][BM];
+  __shared__ RowInfo s_rows[3][BM];
+  __shared__ float2 s_ln[8][BM];              // (mu, rstd) per tile row, ring over this CTA's tiles (producers run ahead of the epilogue)
   __shared__ float s_stat[NWG][16];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -93,11 +94,12 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
     const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int n_items = my_tiles * KC;
     int last_table = -1;
+    float ln_s[4] = {0.f, 0.f, 0.f, 0.f}, ln_ss[4] = {0.f, 0.f, 0.f, 0.f};   // LayerNorm partial sums of this thread's 4 rows
     const int xshift = (BN == 64) ? p.exp_shift : 0;      // experiment: operand rows stored `xshift` rows down
     uint32_t it = 0;
     long long tp_wait = 0, tp_work = 0, tp_load = 0;       // trace accumulators (registers; written once at the end)
 
-    // row table of this CTA's T-th tile (ring of 4: prefetch runs at most 2 items = 2 tiles ahead of the stores)
+    // row table of this CTA's T-th tile (ring of 3: prefetch runs at most 2 items = 2 tiles ahead of the stores)
     auto ensure_table = [&](int T) {
       if (T <= last_table) return;
       const int tile = blockIdx.x + T * gridDim.x;
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
         } else {
           ri.pix = -1; ri.iy = 0; ri.ix = 0;
         }
-        s_rows[T & 3][tid] = ri;
+        s_rows[T % 3][tid] = ri;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       last_table = T;
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
       const long long tl0 = trl ? clock64() : 0;
       const int T = g / KC, kc = g - T * KC;
       ensure_table(T);
-      const RowInfo* rows = s_rows[T & 3];
+      const RowInfo* rows = s_rows[T % 3];
       const int tap = kc / chunks_per_tap;
       const int c0 = (kc - tap * chunks_per_tap) * BKP;
       const int dy = p.dy[tap], dx = p.dx[tap];
@@ -298,8 +300,10 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
     constexpr int EN = 64;                                 // columns per epilogue thread
     float* wbuf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + ((wg * 4 + ew) * 32 * 20);
     uint32_t cg = 0;
+    int Te = -1;
     long long te_wait = 0, te_final = 0, te_drain = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      ++Te;
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN + wg * EN;
       float acc[EN];
 #pragma unroll
@@ -390,7 +394,9 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
         }
       } else {
         // LayerNorm fold (see gemm.cu): v = rstd * (acc - mu * colsum)
-        const float mu = p.rowstats[2 * (size_t)srow], rs = p.rowstats[2 * (size_t)srow + 1];
+        float mu, rs;
+        if (p.ln_inline) { const float2 st = s_ln[Te & 7][row_in_tile]; mu = st.x; rs = st.y; }
+        else { mu = p.rowstats[2 * (size_t)srow]; rs = p.rowstats[2 * (size_t)srow + 1]; }
 #pragma unroll
         for (int i = 0; i < EN; ++i) acc[i] = rs * (acc[i] - mu * p.wsum[n0 + i]);
         if (EPI == EPI_QKV_TEMPORAL) {

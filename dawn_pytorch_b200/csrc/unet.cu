@@ -485,6 +485,20 @@ int Ctx::gemm(const GemmParams& p, int epi, int cat) {
 
 int tap(Ctx& c, const std::string& name, const Act& a);
 
+// LayerNorm-folded 1x1 GEMM: on the tcgen05 path the producers compute the row statistics themselves (no separate
+// rowstats launch, no second read of the input); otherwise run rowstats_kernel into the global buffer.
+int ln_gemm(Ctx& c, GemmParams& p, int epi, int cat, const float* x, int ldx, int C, int rows) {
+  dawn_unet* h = c.h;
+  p.ln_inline = 0; p.rowstats = h->ROWSTATS;
+  if (h->use_tc && p.Bimg != nullptr && tc_gemm_supported(p, epi) && p.ntaps == 1) {
+    p.ln_inline = 1; p.rowstats = nullptr;
+  } else {
+    ProfScope ps(c, PC_ROWSTATS, 0, 4.0 * rows * C);
+    DAWN_TRY(launch_rowstats(x, ldx, C, rows, 1e-5f, h->ROWSTATS, c.st));
+  }
+  return c.gemm(p, epi, cat);
+}
+
 // conv k x k, stride 1, same padding, + bias, optional GroupNorm statistics slot
 int conv_same(Ctx& c, const Act& in, const ConvW& w, int k, const Act& out, int stat_slot) {
   GemmParams p; base_params(p, in, c.h->F);
@@ -513,14 +527,10 @@ int resblock(Ctx& c, const ResBlockW& r, const Act& x, const Act& out) {
   const double count = (double)h->sh_Fglobal * P * (r.co / 8);     // GroupNorm statistics span the WHOLE clip (U:230)
   if (r.cond) {
     // cross-attention gates from the raw block input (U:454-463): LayerNorm_img folded into the q projection
-    {
-      ProfScope ps(c, PC_ROWSTATS, 0, 4.0 * M * x.C);
-      DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
-    }
     GemmParams p; base_params(p, x, F);
     p.B = r.Wq; p.Bimg = r.Wq_img; p.tc_scale = 1.0f / (kTcActScale * r.Wq_scale); p.ldb = 192; p.N = 192; p.K = r.ci;
-    p.rowstats = h->ROWSTATS; p.wsum = r.wsumq; p.kq = r.kq; p.nkq = r.nkq; p.gates = h->GATES;
-    DAWN_TRY(c.gemm(p, EPI_CA_GATE, PC_CA_GATE));
+    p.wsum = r.wsumq; p.kq = r.kq; p.nkq = r.nkq; p.gates = h->GATES;
+    DAWN_TRY(ln_gemm(c, p, EPI_CA_GATE, PC_CA_GATE, x.p, x.ld, x.C, M));
     ProfScope ps(c, PC_CA_RSTD, 0, 4.0 * M * 56);
     DAWN_TRY(launch_ca_rstd(h->GATES, r.G, M, P, h->WT, c.st));
   }
@@ -594,18 +604,14 @@ int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const st
     xe = Act{h->XE, x.C, x.C, x.H, x.W};
   }
   {
-    ProfScope ps(c, PC_ROWSTATS, 0, 4.0 * Me * x.C);
-    DAWN_TRY(launch_rowstats(xe.p, xe.ld, xe.C, Me, 1e-5f, h->ROWSTATS, c.st));
-  }
-  {
     GemmParams p; base_params(p, xe, Fe);
     p.B = w.Wqkv; p.Bimg = w.Wqkv_img; p.tc_scale = 1.0f / (kTcActScale * w.Wqkv_scale); p.ldb = 768; p.N = 768; p.K = x.C;
-    p.rowstats = h->ROWSTATS; p.wsum = w.wsum; p.rot = h->ROT;
+    p.wsum = w.wsum; p.rot = h->ROT;
     p.Out = h->QKV; p.ldo = 768;
     p.perm_pb = pb; p.perm_F = Fe; p.perm_in = 1; p.perm_out = 0;
     // output rows are written in plain order m (the permuted enumeration): treat the output as one M x 1 "image"
     p.OH = Me; p.OW = 1; p.OHs = Me; p.OWs = 1; p.IH = Me; p.IW = 1;
-    DAWN_TRY(c.gemm(p, EPI_QKV_TEMPORAL, PC_QKV));
+    DAWN_TRY(ln_gemm(c, p, EPI_QKV_TEMPORAL, PC_QKV, xe.p, xe.ld, xe.C, Me));
   }
   {
     AttnArgs a{};
@@ -635,15 +641,11 @@ int mid_spatial_attn(Ctx& c, const AttnW& w, const Act& x, const std::string& na
   dawn_unet* h = c.h;
   const int F = h->F, P = x.H * x.W, M = F * P;
   {
-    ProfScope ps(c, PC_ROWSTATS, 0, 4.0 * M * x.C);
-    DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
-  }
-  {
     GemmParams p; base_params(p, x, F);
     p.B = w.Wqkv; p.Bimg = w.Wqkv_img; p.tc_scale = 1.0f / (kTcActScale * w.Wqkv_scale); p.ldb = 768; p.N = 768; p.K = x.C;
-    p.rowstats = h->ROWSTATS; p.wsum = w.wsum;
+    p.wsum = w.wsum;
     p.Out = h->QKV; p.ldo = 768;
-    DAWN_TRY(c.gemm(p, EPI_QKV_MID, PC_QKV));
+    DAWN_TRY(ln_gemm(c, p, EPI_QKV_MID, PC_QKV, x.p, x.ld, x.C, M));
   }
   {
     AttnArgs a{};
@@ -669,15 +671,11 @@ int sla(Ctx& c, const SlaW& w, const Act& x, const std::string& name) {
   dawn_unet* h = c.h;
   const int F = h->F, P = x.H * x.W, M = F * P;
   {
-    ProfScope ps(c, PC_ROWSTATS, 0, 4.0 * M * x.C);
-    DAWN_TRY(launch_rowstats(x.p, x.ld, x.C, M, 1e-5f, h->ROWSTATS, c.st));
-  }
-  {
     GemmParams p; base_params(p, x, F);
     p.B = w.Wqkv; p.Bimg = w.Wqkv_img; p.tc_scale = 1.0f / (kTcActScale * w.Wqkv_scale); p.ldb = 768; p.N = 768; p.K = x.C;
-    p.rowstats = h->ROWSTATS; p.wsum = w.wsum; p.q_post_scale = 1.0f / sqrtf(32.0f);
+    p.wsum = w.wsum; p.q_post_scale = 1.0f / sqrtf(32.0f);
     p.Out = h->QKV; p.ldo = 768;
-    DAWN_TRY(c.gemm(p, EPI_QKV_SLA, PC_QKV));
+    DAWN_TRY(ln_gemm(c, p, EPI_QKV_SLA, PC_QKV, x.p, x.ld, x.C, M));
   }
   const int ldb = round_up(x.C, 64);
   {
