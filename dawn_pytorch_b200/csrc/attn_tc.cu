@@ -148,11 +148,11 @@ __global__ void __launch_bounds__(ATHREADS) attention_tc_kernel(AttnArgs a) {
     for (int b = 0; b < NQB; ++b) {
       const int i0 = q0 + (warp + (ATHREADS / 32) * b) * 16;
       if (i0 >= q1) continue;
-      // 32-key blocks this query block needs inside the chunk
-      int kb_lo = 0, kb_hi = (nk + 31) / 32;
-      if (banded) { kb_lo = (i0 - q0) / 32; kb_hi = min(kb_hi, (i0 - q0 + 16 + 2 * band + 31) / 32); }
-      for (int kb = kb_lo; kb < kb_hi; ++kb) {
-        const int kr0 = kb * 32;                                   // first key row (in the chunk) of this block
+      // 32-key blocks this query block needs inside the chunk.  Banded: its 16 queries see keys [i0-band, i0+15+band],
+      // i.e. chunk rows [i0-q0, i0-q0+16+2*band): start exactly there (rows need no alignment) -> 3 blocks instead of 4.
+      int kr_lo = 0, kr_hi = nk;
+      if (banded) { kr_lo = i0 - q0; kr_hi = min(nk, i0 - q0 + 16 + 2 * band); }
+      for (int kr0 = kr_lo; kr0 < kr_hi; kr0 += 32) {
         // ---------------- S = Q K^T  (4 n-tiles of 8 keys, k = 32 dims in 2 steps, 3-term split)
         float s[4][4];
 #pragma unroll
@@ -182,7 +182,9 @@ __global__ void __launch_bounds__(ATHREADS) attention_tc_kernel(AttnArgs a) {
             const int i = i0 + g + ((c & 2) ? 8 : 0);
             const int j = kc0 + kr0 + n * 8 + 2 * t + (c & 1);
             const int rel = j - i;
-            const bool v = (j >= 0) && (j < a.L) && (kr0 + n * 8 + 2 * t + (c & 1) < nk) && (!banded || (rel <= band && rel >= -band));
+            // banded: |rel| <= band already implies the row lies inside the staged chunk
+            const bool v = banded ? ((unsigned)(rel + band) <= (unsigned)(2 * band)) && ((unsigned)j < (unsigned)a.L)
+                                  : ((j < a.L) && (kr0 + n * 8 + 2 * t + (c & 1) < nk));
             ok[n][c] = v;
             if (v) {
               if (a.bias != nullptr) s[n][c] += s_bias[rel + band];

@@ -21,7 +21,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // cycles per panel).  Ordering of the operand writes is provided by the preceding fence.proxy.async; the consumer side
 // (mbarrier try_wait, acquire) is unchanged.
 __device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)));
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");   // compiler barrier only
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -119,7 +119,17 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, ui
 // projection's output stream at ~1.6 TB/s).
 __device__ __forceinline__ void store_rows_coalesced(float* wbuf, const float (&acc)[64], float* out, size_t opix, int ldo,
                                                      int n0, bool rv, int lane) {
-  const uint32_t op_lo = (uint32_t)opix, op_hi = (uint32_t)((unsigned long long)opix >> 32);
+  // destination rows of this lane in the read-back phase: r = lane/4 + 8k (fetched once from the owning lanes)
+  float* dst[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = (lane >> 2) + 8 * k;
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)opix, r);
+    const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)((unsigned long long)opix >> 32), r);
+    const int ok = __shfl_sync(0xffffffffu, rv ? 1 : 0, r);
+    const size_t px = ((size_t)hi << 32) | lo;
+    dst[k] = ok ? (out + px * ldo + n0 + (lane & 3) * 4) : nullptr;
+  }
 #pragma unroll
   for (int pass = 0; pass < 4; ++pass) {
     __syncwarp();
@@ -130,18 +140,12 @@ __device__ __forceinline__ void store_rows_coalesced(float* wbuf, const float (&
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int r = (lane >> 2) + 8 * k, c4 = lane & 3;
-      const float4 v = *reinterpret_cast<const float4*>(wbuf + r * 20 + c4 * 4);
-      const uint32_t lo = __shfl_sync(0xffffffffu, op_lo, r), hi = __shfl_sync(0xffffffffu, op_hi, r);
-      const int ok = __shfl_sync(0xffffffffu, rv ? 1 : 0, r);
-      if (ok) {
-        const size_t px = ((size_t)hi << 32) | lo;
-        *reinterpret_cast<float4*>(out + px * ldo + n0 + pass * 16 + c4 * 4) = v;
-      }
+      const int r = (lane >> 2) + 8 * k;
+      const float4 v = *reinterpret_cast<const float4*>(wbuf + r * 20 + (lane & 3) * 4);
+      if (dst[k]) *reinterpret_cast<float4*>(dst[k] + pass * 16) = v;
     }
   }
 }
-
 
 }  // namespace tc
 }  // namespace dawn

@@ -329,9 +329,6 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
         if (tr) te_drain += clock64() - t0;
       }
 
-#pragma unroll
-      for (int i = 0; i < EN; ++i) acc[i] *= p.tc_scale;       // undo the exact power-of-two operand pre-scales
-
       // ---------------------------------------------------------- final epilogue: this thread owns row m
       const bool tr_e = (p.trace != nullptr) && blockIdx.x == 0 && etid == 0;
       const long long te0 = tr_e ? clock64() : 0;
@@ -350,13 +347,18 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
       const int srow = p.perm_in ? seq_blocked_pixel(mc, p.perm_pb, p.perm_F, p.P) : mc;     // pixel behind this row
 
       if (EPI == EPI_PLAIN) {
+        const float sc = p.tc_scale;                          // undoes the exact power-of-two weight pre-scale
         if (p.bias) {
           const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
           for (int i = 0; i < EN / 4; ++i) {
             const float4 b = __ldg(bp + i);
-            acc[4 * i] += b.x; acc[4 * i + 1] += b.y; acc[4 * i + 2] += b.z; acc[4 * i + 3] += b.w;
+            acc[4 * i] = fmaf(acc[4 * i], sc, b.x); acc[4 * i + 1] = fmaf(acc[4 * i + 1], sc, b.y);
+            acc[4 * i + 2] = fmaf(acc[4 * i + 2], sc, b.z); acc[4 * i + 3] = fmaf(acc[4 * i + 3], sc, b.w);
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < EN; ++i) acc[i] *= sc;
         }
         if (rv && p.Res) {
           const float4* rp = reinterpret_cast<const float4*>(p.Res + opix * p.ldr + n0);
@@ -397,18 +399,31 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
         float mu, rs;
         if (p.ln_inline) { const float2 st = s_ln[Te & 7][row_in_tile]; mu = st.x; rs = st.y; }
         else { mu = p.rowstats[2 * (size_t)srow]; rs = p.rowstats[2 * (size_t)srow + 1]; }
+        {
+          const float fa = rs * p.tc_scale, fb = -rs * mu;     // rstd * (scale*acc - mu*colsum)
+          const float4* wp = reinterpret_cast<const float4*>(p.wsum + n0);
 #pragma unroll
-        for (int i = 0; i < EN; ++i) acc[i] = rs * (acc[i] - mu * p.wsum[n0 + i]);
+          for (int i = 0; i < EN / 4; ++i) {
+            const float4 w = __ldg(wp + i);
+            acc[4 * i] = fmaf(fb, w.x, fa * acc[4 * i]); acc[4 * i + 1] = fmaf(fb, w.y, fa * acc[4 * i + 1]);
+            acc[4 * i + 2] = fmaf(fb, w.z, fa * acc[4 * i + 2]); acc[4 * i + 3] = fmaf(fb, w.w, fa * acc[4 * i + 3]);
+          }
+        }
         if (EPI == EPI_QKV_TEMPORAL) {
           if (n0 < 512) {
             const int fr = srow / p.P;
+            // this row's 16 (cos, sin) pairs serve both heads of the 64-column slice
+            const float4* rp = reinterpret_cast<const float4*>(p.rot + (size_t)fr * 32);
 #pragma unroll
-            for (int i = 0; i < EN; i += 2) {
-              const int pi = ((n0 + i) & 31) >> 1;
-              const float2 cs = *reinterpret_cast<const float2*>(p.rot + (size_t)(fr * 16 + pi) * 2);
-              const float x0 = acc[i], x1 = acc[i + 1];
-              acc[i] = x0 * cs.x - x1 * cs.y;
-              acc[i + 1] = x1 * cs.x + x0 * cs.y;
+            for (int j = 0; j < 8; ++j) {
+              const float4 cs = __ldg(rp + j);                    // pairs 2j, 2j+1
+#pragma unroll
+              for (int hd = 0; hd < EN / 32; ++hd) {
+                const int i = hd * 32 + 4 * j;
+                const float x0 = acc[i], x1 = acc[i + 1], x2 = acc[i + 2], x3 = acc[i + 3];
+                acc[i] = x0 * cs.x - x1 * cs.y; acc[i + 1] = x1 * cs.x + x0 * cs.y;
+                acc[i + 2] = x2 * cs.z - x3 * cs.w; acc[i + 3] = x3 * cs.z + x2 * cs.w;
+              }
             }
           }
         } else if (EPI == EPI_QKV_SLA) {
