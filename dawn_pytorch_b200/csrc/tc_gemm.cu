@@ -34,7 +34,7 @@ constexpr int NPROD = 256;              // producer threads (warps 0-7)
 template <int BN>
 struct Cfg {
   static constexpr int NWG = BN / 64;                        // epilogue warpgroups
-  static constexpr int A_PANEL = (BN == 64) ? 18 * 1024 : A_PANEL_MIN;   // BN = 64: 16 spare rows for shifted-window experiments
+  static constexpr int A_PANEL = A_PANEL_MIN;
   static constexpr int B_PANEL = BN * 128;
   static constexpr int STAGE_BYTES = 2 * A_PANEL + 2 * B_PANEL;
   static constexpr int STAGES = (BN == 64) ? 4 : 3;
@@ -95,7 +95,6 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
     const int n_items = my_tiles * KC;
     int last_table = -1;
     float ln_s[4] = {0.f, 0.f, 0.f, 0.f}, ln_ss[4] = {0.f, 0.f, 0.f, 0.f};   // LayerNorm partial sums of this thread's 4 rows
-    const int xshift = (BN == 64) ? p.exp_shift : 0;      // experiment: operand rows stored `xshift` rows down
     uint32_t it = 0;
     long long tp_wait = 0, tp_work = 0, tp_load = 0;       // trace accumulators (registers; written once at the end)
 
@@ -163,14 +162,32 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
         split_f16x2(v[2 * q].z, v[2 * q].w, h[1], l[1]);
         split_f16x2(v[2 * q + 1].x, v[2 * q + 1].y, h[2], l[2]);
         split_f16x2(v[2 * q + 1].z, v[2 * q + 1].w, h[3], l[3]);
-        uint32_t off;
-        {
-          const int rr = r0 + 32 * q, rs = rr + (xshift & 15);
-          const int ph = ((xshift >> 4) & 2) ? (rr & 7) : (rs & 7);         // mode bit 1: swizzle phase relative to the window start
-          off = (uint32_t)((rs >> 3) * 1024 + (rs & 7) * 128 + ((c16 ^ ph) << 4));
-        }
+        const uint32_t off = swz(r0 + 32 * q, c16);
         *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+        if (p.ln_inline) {
+          const float4 a = v[2 * q], b = v[2 * q + 1];
+          ln_s[q] += ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+          ln_ss[q] += ((a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w)) + ((b.x * b.x + b.y * b.y) + (b.z * b.z + b.w * b.w));
+        }
+      }
+      if (p.ln_inline) {
+        const int Ts = (int)(it / (uint32_t)KC), kcs = (int)(it - (uint32_t)Ts * KC);
+        if (kcs == KC - 1) {                                   // the row is complete: reduce over the 8 lanes that share it
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float sx = ln_s[q], sxx = ln_ss[q];
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sxx += __shfl_xor_sync(0xffffffffu, sxx, o); }
+            if (c16 == 0) {
+              const float inv = 1.0f / (float)p.K;
+              const float mu = sx * inv;
+              const float var = fmaxf(sxx * inv - mu * mu, 0.f);
+              s_ln[Ts & 7][r0 + 32 * q] = make_float2(mu, 1.0f / sqrtf(var + 1e-5f));
+            }
+            ln_s[q] = 0.f; ln_ss[q] = 0.f;
+          }
+        }
       }
       // no proxy fence here: fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and would make every
       // producer thread drain its outstanding prefetch loads once per panel (measured ~1000 cycles).  The st.shared
@@ -263,10 +280,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
           fence_proxy_async();          // generic-proxy operand writes of the producers -> async proxy (see store_item)
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-          const int xs = (BN == 64) ? p.exp_shift : 0;
-          const int xsh = xs & 15, xbo = ((xs >> 4) & 1) ? 0 : xsh;              // mode bit 0: base_offset forced to 0
-          const uint64_t ahi = make_desc(sa + xsh * 128) | ((uint64_t)(xbo & 7) << 49);
-          const uint64_t alo = make_desc(sa + A_PANEL + xsh * 128) | ((uint64_t)(xbo & 7) << 49);
+          const uint64_t ahi = make_desc(sa), alo = make_desc(sa + A_PANEL);
           const uint64_t bhi = make_desc(sa + 2 * A_PANEL), blo = make_desc(sa + 2 * A_PANEL + B_PANEL);
           const uint32_t d = tmem_base + buf * BN;
 #pragma unroll
