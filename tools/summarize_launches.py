@@ -8,9 +8,12 @@ import sys
 def short(name):
     name = re.sub(r"^void\s+", "", name)
     m = re.search(r"gemm_kernel<\(?(?:int\))?(\d+)>", name) or re.search(r"gemm_kernel<(\d+)>", name)
+    if "tc_gemm_kernel" in name:
+        m2 = re.search(r"tc_gemm_kernel<[^0-9]*(\d+)[^0-9]+(\d+)", name)
+        return f"dawn::tc_gemm_kernel<EPI={m2.group(1)},BN={m2.group(2)}>" if m2 else "dawn::tc_gemm_kernel"
     if "gemm_kernel" in name:
         epi = re.search(r"gemm_kernel<[^0-9]*(\d+)", name)
-        return f"dawn::gemm_kernel<EPI={epi.group(1) if epi else '?'}>"
+        return f"dawn::gemm_kernel<EPI={epi.group(1) if epi else '?'}> (mma.sync)"
     name = re.sub(r"\(.*$", "", name)
     name = name.replace("dawn::(anonymous namespace)::", "dawn::")
     return name[:90]
