@@ -1,0 +1,431 @@
+// Fused temporal attention for 64-channel levels (reference U:648-725 == LA:275-342 wrapped in Residual(PreNorm(...)),
+// U:763-765): one CTA owns ONE PIXEL's whole frame sequence and does everything on chip:
+//
+//   x[:, p, :] (F x 64 fp32) -> LayerNorm statistics -> fp16 hi/lo split in shared memory
+//   per head h:   K_h, V_h, Q_h = LN-folded projections (mma.sync m16n8k16, 3-term FP16 split, fp32 accumulate)
+//                 rotary on q, k (registers)  ->  K_h (row-major) and V_h^T to shared memory as fp16 hi/lo; Q_h stays in registers
+//                 banded (+-band, + relative bias) softmax attention (FlashAttention-2 style, as attn_tc.cu)
+//                 y += O_h * Wout_h            (accumulator layout of O == A-operand layout of the next MMA)
+//   out[:, p, :] = x + y
+//
+// q/k/v and the attention output never reach HBM (the unfused path wrote 2.5 GB of q|k|v per level-0 layer and read it back),
+// the three launches (qkv GEMM, attention, out-projection GEMM) become one.  Warp w owns the 16-frame tiles w and w+8: its Q tiles
+// and its y accumulators live in registers across the whole head loop.
+#include <cuda_fp16.h>
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include "common.cuh"
+#include "kernels.cuh"
+#include "temporal_fused.cuh"
+
+namespace dawn {
+namespace {
+
+constexpr int C = 64;                 // channels of the levels this kernel serves
+constexpr int X_LD = C + 8;           // halfs per x row      (conflict-free A-fragment reads)
+constexpr int W_LD = C + 8;           // halfs per W_h row    (B-fragment reads)
+constexpr int K_LD = 40;              // halfs per K row
+constexpr int WO_LD = 40;             // halfs per Wout_h row ([n = channel][k = head dim])
+constexpr int NTH = 256;
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split2h(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const float h0 = __uint_as_float((__float_as_uint(x0) + 0x1000u) & 0xFFFFE000u);
+  const float h1 = __uint_as_float((__float_as_uint(x1) + 0x1000u) & 0xFFFFE000u);
+  const __half2 h = __floats2half2_rn(h0, h1);
+  const __half2 l = __floats2half2_rn(x0 - h0, x1 - h1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void split1h(float x, __half& hi, __half& lo) {
+  const float h = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  hi = __float2half_rn(h);
+  lo = __float2half_rn(x - h);
+}
+__device__ __forceinline__ uint32_t lds32(const __half* p) { return *reinterpret_cast<const uint32_t*>(p); }
+
+struct Smem {
+  __half *Xh, *Xl, *Wh, *Wl, *Kh, *Kl, *Vh, *Vl, *Oh, *Ol;
+  float *stat, *bias;
+  int v_ld;
+};
+
+__global__ void __launch_bounds__(NTH, 1) temporal_fused_kernel(TemporalFusedArgs a) {
+  extern __shared__ __align__(16) unsigned char tf_smem[];
+  const int F = a.F;                                   // sequence length held on chip (incl. halo frames when sharded)
+  const int Fp = (F + 15) & ~15;                       // padded to whole 16-frame tiles
+  const int KROWS = Fp + 32;                           // key rows incl. zero rows read by the last 32-key block
+  const int v_ld = KROWS + 8;
+  __half* Xh = reinterpret_cast<__half*>(tf_smem);
+  __half* Xl = Xh + Fp * X_LD;
+  __half* Wh = Xl + Fp * X_LD;
+  __half* Wl = Wh + 96 * W_LD;
+  __half* Kh = Wl + 96 * W_LD;
+  __half* Kl = Kh + KROWS * K_LD;
+  __half* Vh = Kl + KROWS * K_LD;
+  __half* Vl = Vh + 32 * v_ld;
+  __half* Oh = Vl + 32 * v_ld;                         // Wout_h hi: [64][WO_LD]
+  __half* Ol = Oh + 64 * WO_LD;
+  float* s_stat = reinterpret_cast<float*>(Ol + 64 * WO_LD);      // [Fp][2]  (mu, rstd)
+  float* s_bias = s_stat + 2 * Fp;                                 // [8][2*band+1]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int pix = blockIdx.x;
+  const int band = a.band;
+  const int nbias = 2 * band + 1;
+
+  // ------------------------------------------------------------------ phase 0: x rows of this pixel, LN statistics, fp16 split
+  for (int i = tid; i < 8 * nbias; i += NTH) s_bias[i] = a.bias[i];
+  {
+    const int l16 = tid & 15;                           // 16 lanes x float4 = one 64-channel row
+    for (int f0 = 0; f0 < Fp; f0 += NTH / 16) {
+      const int f = f0 + (tid >> 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f < F) v = __ldg(reinterpret_cast<const float4*>(a.x + ((size_t)f * a.P + pix) * a.ldx) + l16);
+      float s = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mu = s * (1.0f / C);
+      const float d0 = v.x - mu, d1 = v.y - mu, d2 = v.z - mu, d3 = v.w - mu;
+      float ss = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      if (f < Fp) {
+        if (l16 == 0) { s_stat[2 * f] = mu; s_stat[2 * f + 1] = 1.0f / sqrtf(ss * (1.0f / C) + 1e-5f); }
+        uint32_t h0, l0, h1, l1;
+        split2h(v.x, v.y, h0, l0); split2h(v.z, v.w, h1, l1);
+        *reinterpret_cast<uint2*>(&Xh[f * X_LD + l16 * 4]) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(&Xl[f * X_LD + l16 * 4]) = make_uint2(l0, l1);
+      }
+    }
+    // zero the key rows / value columns beyond the sequence once (masked lanes must multiply finite numbers)
+    for (int i = tid; i < (KROWS - F) * K_LD; i += NTH) { Kh[F * K_LD + i] = __float2half(0.f); Kl[F * K_LD + i] = __float2half(0.f); }
+    for (int i = tid; i < 32 * (v_ld - F); i += NTH) {
+      const int d = i / (v_ld - F), c = F + i % (v_ld - F);
+      Vh[d * v_ld + c] = __float2half(0.f); Vl[d * v_ld + c] = __float2half(0.f);
+    }
+  }
+
+  const int ntiles = Fp >> 4;
+  // y accumulators of this warp's (up to) two 16-frame tiles: [tile][8 n-tiles of 8 channels][4]
+  float y[2][8][4];
+#pragma unroll
+  for (int b = 0; b < 2; ++b)
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) y[b][n][c] = 0.f;
+
+  for (int head = 0; head < 8; ++head) {
+    __syncthreads();                                    // previous head's K/V/W no longer needed (also orders phase 0)
+    // ---------------------------------------------------------------- (a) this head's weights: W'_h [96][64], Wout_h [64][32] (fp16 hi | lo)
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(a.Wqkv + (size_t)head * 2 * 96 * C);     // hi then lo, dense [96][64]
+      for (int i = tid; i < 2 * 96 * C / 8; i += NTH) {
+        const int part = i / (96 * C / 8), j = i - part * (96 * C / 8);
+        const int r = j / (C / 8), c8 = j - r * (C / 8);
+        *reinterpret_cast<uint4*>((part ? Wl : Wh) + r * W_LD + c8 * 8) = __ldg(src + i);
+      }
+      const uint4* so = reinterpret_cast<const uint4*>(a.Wout + (size_t)head * 2 * 64 * 32);      // hi then lo, dense [64][32]
+      for (int i = tid; i < 2 * 64 * 32 / 8; i += NTH) {
+        const int part = i / (64 * 32 / 8), j = i - part * (64 * 32 / 8);
+        const int r = j >> 2, c8 = j & 3;
+        *reinterpret_cast<uint4*>((part ? Ol : Oh) + r * WO_LD + c8 * 8) = __ldg(so + i);
+      }
+    }
+    __syncthreads();
+    const float* wsum = a.wsum + head * 32;             // column sums of W' (fp32), layout [q 256 | k 256 | v 256]
+
+    // ---------------------------------------------------------------- (b,c,d) projections of this warp's tiles
+    uint32_t qh[2][2][4], ql[2][2][4];                  // Q tiles as A fragments (fp16 hi / lo), 2 k16 steps
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int tile = warp + 8 * b;
+      if (tile >= ntiles) continue;
+      const int f0 = tile * 16;
+      // A fragments of x for the 4 k16 steps (hi and lo)
+      uint32_t xa_h[4][4], xa_l[4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const __half* r0p = Xh + (f0 + g) * X_LD + ks * 16 + 2 * t;
+        const __half* r0l = Xl + (f0 + g) * X_LD + ks * 16 + 2 * t;
+        xa_h[ks][0] = lds32(r0p); xa_h[ks][1] = lds32(r0p + 8 * X_LD); xa_h[ks][2] = lds32(r0p + 8); xa_h[ks][3] = lds32(r0p + 8 * X_LD + 8);
+        xa_l[ks][0] = lds32(r0l); xa_l[ks][1] = lds32(r0l + 8 * X_LD); xa_l[ks][2] = lds32(r0l + 8); xa_l[ks][3] = lds32(r0l + 8 * X_LD + 8);
+      }
+      const float mu0 = s_stat[2 * (f0 + g)], rs0 = s_stat[2 * (f0 + g) + 1];
+      const float mu1 = s_stat[2 * (f0 + g + 8)], rs1 = s_stat[2 * (f0 + g + 8) + 1];
+      const int fr0 = f0 + g, fr1 = f0 + g + 8;         // frame (= rotary position index into a.rot) of rows g / g+8
+#pragma unroll
+      for (int part = 2; part >= 0; --part) {           // 2: v, 1: k, 0: q  (q last: its fragments stay live)
+        float acc[4][4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[n][c] = 0.f;
+          const int wrow = part * 32 + n * 8 + g;       // row of W'_h = output column
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const int off = wrow * W_LD + ks * 16 + 2 * t;
+            const uint32_t bh0 = lds32(Wh + off), bh1 = lds32(Wh + off + 8);
+            const uint32_t bl0 = lds32(Wl + off), bl1 = lds32(Wl + off + 8);
+            mma16816(acc[n], xa_l[ks], bh0, bh1);
+            mma16816(acc[n], xa_h[ks], bl0, bl1);
+            mma16816(acc[n], xa_h[ks], bh0, bh1);
+          }
+          // LayerNorm fold + weight pre-scale:  rstd * (acc / wscale - mu * colsum)
+          const float w0 = __ldg(wsum + part * 256 + n * 8 + 2 * t), w1 = __ldg(wsum + part * 256 + n * 8 + 2 * t + 1);
+          acc[n][0] = rs0 * (acc[n][0] * a.inv_wscale - mu0 * w0);
+          acc[n][1] = rs0 * (acc[n][1] * a.inv_wscale - mu0 * w1);
+          acc[n][2] = rs1 * (acc[n][2] * a.inv_wscale - mu1 * w0);
+          acc[n][3] = rs1 * (acc[n][3] * a.inv_wscale - mu1 * w1);
+          if (part < 2) {                                // rotary on q and k: interleaved pair (2i, 2i+1), pair index = n*4 + t
+            const float2 cs0 = *reinterpret_cast<const float2*>(a.rot + ((size_t)min(fr0, F - 1) * 16 + n * 4 + t) * 2);
+            const float2 cs1 = *reinterpret_cast<const float2*>(a.rot + ((size_t)min(fr1, F - 1) * 16 + n * 4 + t) * 2);
+            const float x0 = acc[n][0], x1 = acc[n][1], x2 = acc[n][2], x3 = acc[n][3];
+            acc[n][0] = x0 * cs0.x - x1 * cs0.y; acc[n][1] = x1 * cs0.x + x0 * cs0.y;
+            acc[n][2] = x2 * cs1.x - x3 * cs1.y; acc[n][3] = x3 * cs1.x + x2 * cs1.y;
+          }
+        }
+        if (part == 1) {                                 // K rows (row-major, fp16 hi/lo)
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            uint32_t h0, l0, h1, l1;
+            split2h(acc[n][0], acc[n][1], h0, l0); split2h(acc[n][2], acc[n][3], h1, l1);
+            *reinterpret_cast<uint32_t*>(&Kh[fr0 * K_LD + n * 8 + 2 * t]) = h0;
+            *reinterpret_cast<uint32_t*>(&Kl[fr0 * K_LD + n * 8 + 2 * t]) = l0;
+            *reinterpret_cast<uint32_t*>(&Kh[fr1 * K_LD + n * 8 + 2 * t]) = h1;
+            *reinterpret_cast<uint32_t*>(&Kl[fr1 * K_LD + n * 8 + 2 * t]) = l1;
+          }
+        } else if (part == 2) {                          // V transposed: Vt[d][frame]
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              __half hh, ll;
+              split1h(acc[n][c], hh, ll);
+              const int d = n * 8 + 2 * t + (c & 1), fr = (c & 2) ? fr1 : fr0;
+              Vh[d * v_ld + fr] = hh; Vl[d * v_ld + fr] = ll;
+            }
+        } else {                                         // Q: accumulator tiles (2ks, 2ks+1) == A fragment of k16 step ks
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            split2h(acc[2 * ks][0], acc[2 * ks][1], qh[b][ks][0], ql[b][ks][0]);
+            split2h(acc[2 * ks][2], acc[2 * ks][3], qh[b][ks][1], ql[b][ks][1]);
+            split2h(acc[2 * ks + 1][0], acc[2 * ks + 1][1], qh[b][ks][2], ql[b][ks][2]);
+            split2h(acc[2 * ks + 1][2], acc[2 * ks + 1][3], qh[b][ks][3], ql[b][ks][3]);
+          }
+        }
+      }
+    }
+    __syncthreads();                                    // K_h, V_h^T of every frame are in shared memory
+
+    // ---------------------------------------------------------------- (e) banded attention + (f) out-projection per own tile
+    const float* bias = s_bias + head * nbias + band;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int tile = warp + 8 * b;
+      if (tile >= ntiles) continue;
+      const int i0 = tile * 16;
+      if (i0 >= a.q_hi || i0 + 16 <= a.q_lo) continue;  // tile holds no frame whose output is needed (halo tile)
+      float o[4][4], mrow[2] = {-1e30f, -1e30f}, lrow[2] = {0.f, 0.f};
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[n][c] = 0.f;
+      const int kr_lo = max(0, i0 - band), kr_hi = min(F, i0 + 16 + band);
+      for (int kr0 = kr_lo; kr0 < kr_hi; kr0 += 32) {
+        float s[4][4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) s[n][c] = 0.f;
+          const int krow = kr0 + n * 8 + g;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const int off = krow * K_LD + ks * 16 + 2 * t;
+            const uint32_t bh0 = lds32(Kh + off), bh1 = lds32(Kh + off + 8);
+            const uint32_t bl0 = lds32(Kl + off), bl1 = lds32(Kl + off + 8);
+            mma16816(s[n], ql[b][ks], bh0, bh1);
+            mma16816(s[n], qh[b][ks], bl0, bl1);
+            mma16816(s[n], qh[b][ks], bh0, bh1);
+          }
+        }
+        float mnew[2] = {mrow[0], mrow[1]};
+        bool ok[4][4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int i = i0 + g + ((c & 2) ? 8 : 0);
+            const int j = kr0 + n * 8 + 2 * t + (c & 1);
+            const int rel = j - i;
+            const bool v = ((unsigned)(rel + band) <= (unsigned)(2 * band)) && (j < F);
+            ok[n][c] = v;
+            if (v) { s[n][c] += bias[rel]; mnew[c >> 1] = fmaxf(mnew[c >> 1], s[n][c]); }
+          }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 1));
+          mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 2));
+        }
+        const float corr0 = __expf(mrow[0] - mnew[0]), corr1 = __expf(mrow[1] - mnew[1]);
+        mrow[0] = mnew[0]; mrow[1] = mnew[1];
+        float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float pv = ok[n][c] ? __expf(s[n][c] - mnew[c >> 1]) : 0.f;
+            s[n][c] = pv;
+            if (c & 2) ps1 += pv; else ps0 += pv;
+          }
+        lrow[0] = lrow[0] * corr0 + ps0;
+        lrow[1] = lrow[1] * corr1 + ps1;
+        uint32_t ph[2][4], pl[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          split2h(s[2 * ks][0], s[2 * ks][1], ph[ks][0], pl[ks][0]);
+          split2h(s[2 * ks][2], s[2 * ks][3], ph[ks][1], pl[ks][1]);
+          split2h(s[2 * ks + 1][0], s[2 * ks + 1][1], ph[ks][2], pl[ks][2]);
+          split2h(s[2 * ks + 1][2], s[2 * ks + 1][3], ph[ks][3], pl[ks][3]);
+        }
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          const int drow = (n * 8 + g) * v_ld;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const int off = drow + kr0 + ks * 16 + 2 * t;
+            const uint32_t bh0 = lds32(Vh + off), bh1 = lds32(Vh + off + 8);
+            const uint32_t bl0 = lds32(Vl + off), bl1 = lds32(Vl + off + 8);
+            mma16816(acc, pl[ks], bh0, bh1);
+            mma16816(acc, ph[ks], bl0, bl1);
+            mma16816(acc, ph[ks], bh0, bh1);
+          }
+          o[n][0] = o[n][0] * corr0 + acc[0]; o[n][1] = o[n][1] * corr0 + acc[1];
+          o[n][2] = o[n][2] * corr1 + acc[2]; o[n][3] = o[n][3] * corr1 + acc[3];
+        }
+      }
+      // normalise
+      float l0 = lrow[0], l1 = lrow[1];
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+      // (f) y_tile += O_h (16 x 32) * Wout_h^T (32 x 64): O's accumulator tiles (2ks, 2ks+1) == A fragment of k16 step ks
+      uint32_t oh[2][4], ol[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        split2h(o[2 * ks][0] * inv0, o[2 * ks][1] * inv0, oh[ks][0], ol[ks][0]);
+        split2h(o[2 * ks][2] * inv1, o[2 * ks][3] * inv1, oh[ks][1], ol[ks][1]);
+        split2h(o[2 * ks + 1][0] * inv0, o[2 * ks + 1][1] * inv0, oh[ks][2], ol[ks][2]);
+        split2h(o[2 * ks + 1][2] * inv1, o[2 * ks + 1][3] * inv1, oh[ks][3], ol[ks][3]);
+      }
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const int wrow = (n * 8 + g) * WO_LD;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const int off = wrow + ks * 16 + 2 * t;
+          const uint32_t bh0 = lds32(Oh + off), bh1 = lds32(Oh + off + 8);
+          const uint32_t bl0 = lds32(Ol + off), bl1 = lds32(Ol + off + 8);
+          mma16816(acc, ol[ks], bh0, bh1);
+          mma16816(acc, oh[ks], bl0, bl1);
+          mma16816(acc, oh[ks], bh0, bh1);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) y[b][n][c] += acc[c] * a.inv_oscale;     // RN accumulation over heads outside the tensor core
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ out = residual + y for the frames this call owns
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    const int tile = warp + 8 * b;
+    if (tile >= ntiles) continue;
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int f = tile * 16 + g + 8 * hrow;
+      if (f < a.q_lo || f >= a.q_hi) continue;
+      const size_t orow = (size_t)(f - a.q_lo) * a.P + pix;
+      const float* res = a.res + orow * a.ldr;
+      float* dst = a.out + orow * a.ldo;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const float2 r = *reinterpret_cast<const float2*>(res + n * 8 + 2 * t);
+        *reinterpret_cast<float2*>(dst + n * 8 + 2 * t) = make_float2(r.x + y[b][n][2 * hrow], r.y + y[b][n][2 * hrow + 1]);
+      }
+    }
+  }
+}
+
+size_t smem_bytes(int F, int band) {
+  const int Fp = (F + 15) & ~15, KROWS = Fp + 32, v_ld = KROWS + 8;
+  size_t halfs = (size_t)2 * Fp * X_LD + 2 * 96 * W_LD + 2 * KROWS * K_LD + 2 * 32 * v_ld + 2 * 64 * WO_LD;
+  return halfs * 2 + (size_t)(2 * Fp + 8 * (2 * band + 1)) * 4;
+}
+
+}  // namespace
+
+bool temporal_fused_supported(int C_, int F, int band) {
+  if (C_ != C || band > 40 || F < 1) return false;
+  if (((F + 15) >> 4) > 16) return false;                       // 8 warps x 2 tiles of 16 frames
+  return smem_bytes(F, band) <= 225 * 1024;
+}
+
+int launch_temporal_fused(const TemporalFusedArgs& a, cudaStream_t st) {
+  if (!temporal_fused_supported(C, a.F, a.band)) { set_last_error("temporal_fused: unsupported shape"); return -1; }
+  static size_t attr_bytes = 0;
+  const size_t smem = smem_bytes(a.F, a.band);
+  if (smem > attr_bytes) {
+    DAWN_CUDA_OK(cudaFuncSetAttribute(temporal_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_bytes = smem;
+  }
+  temporal_fused_kernel<<<a.P, NTH, smem, st>>>(a);
+  DAWN_LAUNCH_OK();
+  return 0;
+}
+
+// Host packing.  wqkv: [768][64] fp32 rows = output columns (q | k | v blocks of 256, gamma and q-scale folded), wout: [64][256].
+// Produces per head: W'_h [96][64] fp16 hi then lo (rows: q 32, k 32, v 32), Wout_h [64][32] fp16 hi then lo; both pre-scaled by exact
+// powers of two (returned as inverse scales).
+void temporal_fused_pack(const float* wqkv, const float* wout, std::vector<uint16_t>& Wq, std::vector<uint16_t>& Wo, float* inv_wscale,
+                         float* inv_oscale) {
+  auto pow2scale = [](const float* p, size_t n) {
+    float mx = 0.f;
+    for (size_t i = 0; i < n; ++i) mx = std::max(mx, std::fabs(p[i]));
+    int e = 0;
+    if (mx > 0.f) std::frexp(mx, &e);
+    return std::ldexp(1.0f, 11 - e);
+  };
+  const float sq = pow2scale(wqkv, (size_t)768 * 64), so = pow2scale(wout, (size_t)64 * 256);
+  *inv_wscale = 1.0f / sq; *inv_oscale = 1.0f / so;
+  auto put = [](uint16_t* hi, uint16_t* lo, float v) {
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    memcpy(hi, &h, 2); memcpy(lo, &l, 2);
+  };
+  Wq.assign((size_t)8 * 2 * 96 * 64, 0);
+  Wo.assign((size_t)8 * 2 * 64 * 32, 0);
+  for (int h = 0; h < 8; ++h) {
+    uint16_t* qh = Wq.data() + (size_t)h * 2 * 96 * 64; uint16_t* ql = qh + 96 * 64;
+    for (int part = 0; part < 3; ++part)
+      for (int r = 0; r < 32; ++r)
+        for (int k = 0; k < 64; ++k)
+          put(qh + (part * 32 + r) * 64 + k, ql + (part * 32 + r) * 64 + k, wqkv[(size_t)(part * 256 + h * 32 + r) * 64 + k] * sq);
+    uint16_t* oh = Wo.data() + (size_t)h * 2 * 64 * 32; uint16_t* ol = oh + 64 * 32;
+    for (int c = 0; c < 64; ++c)
+      for (int d = 0; d < 32; ++d) put(oh + c * 32 + d, ol + c * 32 + d, wout[(size_t)c * 256 + h * 32 + d] * so);
+  }
+}
+
+}  // namespace dawn

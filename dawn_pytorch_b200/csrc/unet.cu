@@ -15,6 +15,7 @@
 #include "gemm.cuh"
 #include "kernels.cuh"
 #include "tc_gemm.cuh"
+#include "temporal_fused.cuh"
 
 namespace dawn {
 
@@ -111,6 +112,8 @@ struct ResBlockW {
 
 struct AttnW {     // temporal attention / mid spatial attention (U:648-725)
   int C = 0; float Wqkv_scale = 1.f; float *Wqkv = nullptr, *wsum = nullptr, *Wqkv_img = nullptr; ConvW out;
+  // fused per-pixel kernel (temporal_fused.cu), 64-channel levels only
+  uint16_t *fq = nullptr, *fo = nullptr; float f_inv_wscale = 1.f, f_inv_oscale = 1.f;
 };
 struct SlaW {      // spatial linear attention (U:602-627)
   int C = 0; float Wqkv_scale = 1.f; float *Wqkv = nullptr, *wsum = nullptr, *Wqkv_img = nullptr, *WoutT = nullptr, *bout = nullptr;
@@ -131,6 +134,7 @@ struct dawn_unet {
   bool committed = false;
   bool use_tc = true;                          // tcgen05 contraction path (DAWN_TC=0 falls back to mma.sync)
   bool use_conv3 = true;                       // halo-tile tcgen05 3x3 conv (DAWN_TC_CONV3=0 falls back to the per-tap GEMM)
+  bool use_fused_ta = true;                    // fused per-pixel temporal attention on 64-channel levels (DAWN_FUSED_TA=0: unfused)
   bool use_attn_tc = true;                     // tensor-core attention core (DAWN_ATTN_TC=0 falls back to SIMT)
 
   // packed weights
@@ -354,6 +358,18 @@ int pack_attn(dawn_unet* h, const std::string& norm_name, const std::string& fn,
   int ldb = 0;
   DAWN_TRY(pack_linear(h, o, C, 256, nullptr, 1.f, 0, &a->out.w, nullptr, &ldb, &a->out.img, &a->out.img_scale));
   a->out.b = nullptr; a->out.K = 256; a->out.N = C; a->out.ldb = ldb;
+  if (C == 64) {
+    std::vector<float> wq((size_t)768 * C);
+    for (int n = 0; n < 768; ++n)
+      for (int k = 0; k < C; ++k) wq[(size_t)n * C + k] = qkv->data[(size_t)n * C + k] * g->data[k] * (n < 256 ? scale : 1.0f);
+    std::vector<uint16_t> Wq, Wo;
+    temporal_fused_pack(wq.data(), o->data.data(), Wq, Wo, &a->f_inv_wscale, &a->f_inv_oscale);
+    float *dq = nullptr, *dout = nullptr;
+    std::vector<float> tq(Wq.size() / 2), to(Wo.size() / 2);
+    memcpy(tq.data(), Wq.data(), Wq.size() * 2); memcpy(to.data(), Wo.data(), Wo.size() * 2);
+    DAWN_TRY(dev_upload(h, tq, &dq)); DAWN_TRY(dev_upload(h, to, &dout));
+    a->fq = reinterpret_cast<uint16_t*>(dq); a->fo = reinterpret_cast<uint16_t*>(dout);
+  }
   return 0;
 }
 
@@ -602,6 +618,19 @@ int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const st
     }
     DAWN_NCCL_OK(g_nccl.GroupEnd());
     xe = Act{h->XE, x.C, x.C, x.H, x.W};
+  }
+  if (h->use_fused_ta && w.fq && temporal_fused_supported(x.C, Fe, h->cfg.win_width)) {
+    TemporalFusedArgs a{};
+    a.x = xe.p; a.ldx = xe.ld; a.res = x.p; a.ldr = x.ld; a.out = dst.p; a.ldo = dst.ld;
+    a.F = Fe; a.P = P; a.q_lo = hl; a.q_hi = hl + F;
+    a.Wqkv = w.fq; a.Wout = w.fo; a.wsum = w.wsum; a.rot = h->ROT; a.bias = h->rel_bias; a.band = h->cfg.win_width;
+    a.inv_wscale = w.f_inv_wscale; a.inv_oscale = w.f_inv_oscale;
+    double pairs = 0;
+    for (int i = hl; i < hl + F; ++i) pairs += std::min(Fe - 1, i + a.band) - std::max(0, i - a.band) + 1;
+    ProfScope ps(c, PC_ATTN_CORE, 2.0 * Me * x.C * 768 + 4.0 * 32 * 8 * P * pairs + 2.0 * F * P * 256 * x.C,
+                 4.0 * (Me + 2.0 * F * P) * x.C);
+    DAWN_TRY(launch_temporal_fused(a, c.st));
+    return tap(c, name, dst);
   }
   {
     GemmParams p; base_params(p, xe, Fe);
@@ -853,6 +882,7 @@ int dawn_unet_create(const dawn_unet_cfg* cfg, dawn_unet** out) {
   h->cfg = *cfg;
   { const char* e = getenv("DAWN_TC"); h->use_tc = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_ATTN_TC"); h->use_attn_tc = !(e && e[0] == '0'); }
+  { const char* e = getenv("DAWN_FUSED_TA"); h->use_fused_ta = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_TC_CONV3"); h->use_conv3 = !(e && e[0] == '0'); }
   h->nlev = cfg->n_levels;
   h->dims.push_back(cfg->dim);
