@@ -9,8 +9,9 @@
 //   out[:, p, :] = x + y
 //
 // q/k/v and the attention output never reach HBM (the unfused path wrote 2.5 GB of q|k|v per level-0 layer and read it back),
-// the three launches (qkv GEMM, attention, out-projection GEMM) become one.  Warp w owns the 16-frame tiles w and w+8: its Q tiles
-// and its y accumulators live in registers across the whole head loop.
+// the three launches (qkv GEMM, attention, out-projection GEMM) become one.  16 warps: every warp projects K/V of the 16-frame tiles
+// w, w+16, ... and owns ONE query tile whose Q fragments and y accumulators live in registers across the whole head loop.  All
+// operand fragments come from shared memory through ldmatrix.x4 (hi and lo halves of a B fragment in one instruction).
 #include <cuda_fp16.h>
 #include <cmath>
 #include <cstring>
@@ -28,13 +29,20 @@ constexpr int X_LD = C + 8;           // halfs per x row      (conflict-free A-f
 constexpr int W_LD = C + 8;           // halfs per W_h row    (B-fragment reads)
 constexpr int K_LD = 40;              // halfs per K row
 constexpr int WO_LD = 40;             // halfs per Wout_h row ([n = channel][k = head dim])
-constexpr int NTH = 256;
+constexpr int NTH = 512;
+constexpr int NWARP = NTH / 32;
 
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// four 8x8 b16 matrices; lane l supplies the address of row (l & 7) of matrix (l >> 3)
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], const __half* p) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 __device__ __forceinline__ void split2h(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   const float h0 = __uint_as_float((__float_as_uint(x0) + 0x1000u) & 0xFFFFE000u);
@@ -49,13 +57,12 @@ __device__ __forceinline__ void split1h(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(h);
   lo = __float2half_rn(x - h);
 }
-__device__ __forceinline__ uint32_t lds32(const __half* p) { return *reinterpret_cast<const uint32_t*>(p); }
-
-struct Smem {
-  __half *Xh, *Xl, *Wh, *Wl, *Kh, *Kl, *Vh, *Vl, *Oh, *Ol;
-  float *stat, *bias;
-  int v_ld;
-};
+// 3-term split product: acc += a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, b = {hi k0-7, hi k8-15, lo k0-7, lo k8-15}
+__device__ __forceinline__ void mma3(float (&acc)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const uint32_t (&b)[4]) {
+  mma16816(acc, al, b[0], b[1]);
+  mma16816(acc, ah, b[2], b[3]);
+  mma16816(acc, ah, b[0], b[1]);
+}
 
 __global__ void __launch_bounds__(NTH, 1) temporal_fused_kernel(TemporalFusedArgs a) {
   extern __shared__ __align__(16) unsigned char tf_smem[];
@@ -78,6 +85,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_fused_kernel(TemporalFusedArg
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
+  const int lm = lane >> 3, lr = lane & 7;             // ldmatrix: matrix index / row supplied by this lane
   const int pix = blockIdx.x;
   const int band = a.band;
   const int nbias = 2 * band + 1;
@@ -115,14 +123,54 @@ __global__ void __launch_bounds__(NTH, 1) temporal_fused_kernel(TemporalFusedArg
   }
 
   const int ntiles = Fp >> 4;
-  // y accumulators of this warp's (up to) two 16-frame tiles: [tile][8 n-tiles of 8 channels][4]
-  float y[2][8][4];
+  const int qtile = (a.q_lo >> 4) + warp;               // the 16-frame query tile this warp owns (if it holds an owned frame)
+  const bool has_q = qtile * 16 < a.q_hi;
+  float y[8][4];                                        // out-projection accumulators of the query tile: 8 n-tiles of 8 channels
 #pragma unroll
-  for (int b = 0; b < 2; ++b)
+  for (int n = 0; n < 8; ++n)
 #pragma unroll
-    for (int n = 0; n < 8; ++n)
+    for (int c = 0; c < 4; ++c) y[n][c] = 0.f;
+
+  // One projection part (0: q, 1: k, 2: v) of one 16-frame tile: acc = x_tile (16 x 64) * W'_h[part]^T (64 x 32), LayerNorm folded,
+  // rotary applied to q and k.  Four independent accumulator chains (n-tiles) per k16 step.
+  int head_off = 0;                                     // head * 32: column offset inside the q | k | v blocks of wsum
+  auto project = [&](int f0, int part, float (&acc)[4][4]) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) y[b][n][c] = 0.f;
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[n][c] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ah[4], al[4];
+      const int aoff = (f0 + (lm & 1) * 8 + lr) * X_LD + ks * 16 + (lm >> 1) * 8;
+      ldsm4(ah, Xh + aoff);
+      ldsm4(al, Xl + aoff);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        uint32_t b[4];
+        ldsm4(b, ((lm & 2) ? Wl : Wh) + (part * 32 + n * 8 + lr) * W_LD + ks * 16 + (lm & 1) * 8);
+        mma3(acc[n], ah, al, b);
+      }
+    }
+    const float mu0 = s_stat[2 * (f0 + g)], rs0 = s_stat[2 * (f0 + g) + 1];
+    const float mu1 = s_stat[2 * (f0 + g + 8)], rs1 = s_stat[2 * (f0 + g + 8) + 1];
+    const int fr0 = min(f0 + g, F - 1), fr1 = min(f0 + g + 8, F - 1);
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const float2 w = __ldg(reinterpret_cast<const float2*>(a.wsum + part * 256 + head_off + n * 8 + 2 * t));
+      acc[n][0] = rs0 * (acc[n][0] * a.inv_wscale - mu0 * w.x);
+      acc[n][1] = rs0 * (acc[n][1] * a.inv_wscale - mu0 * w.y);
+      acc[n][2] = rs1 * (acc[n][2] * a.inv_wscale - mu1 * w.x);
+      acc[n][3] = rs1 * (acc[n][3] * a.inv_wscale - mu1 * w.y);
+      if (part < 2) {                                    // rotary: interleaved pair (2i, 2i+1), pair index = n*4 + t
+        const float2 cs0 = __ldg(reinterpret_cast<const float2*>(a.rot) + (size_t)fr0 * 16 + n * 4 + t);
+        const float2 cs1 = __ldg(reinterpret_cast<const float2*>(a.rot) + (size_t)fr1 * 16 + n * 4 + t);
+        const float x0 = acc[n][0], x1 = acc[n][1], x2 = acc[n][2], x3 = acc[n][3];
+        acc[n][0] = x0 * cs0.x - x1 * cs0.y; acc[n][1] = x1 * cs0.x + x0 * cs0.y;
+        acc[n][2] = x2 * cs1.x - x3 * cs1.y; acc[n][3] = x3 * cs1.x + x2 * cs1.y;
+      }
+    }
+  };
 
   for (int head = 0; head < 8; ++head) {
     __syncthreads();                                    // previous head's K/V/W no longer needed (also orders phase 0)
@@ -142,219 +190,153 @@ __global__ void __launch_bounds__(NTH, 1) temporal_fused_kernel(TemporalFusedArg
       }
     }
     __syncthreads();
-    const float* wsum = a.wsum + head * 32;             // column sums of W' (fp32), layout [q 256 | k 256 | v 256]
+    head_off = head * 32;
 
-    // ---------------------------------------------------------------- (b,c,d) projections of this warp's tiles
-    uint32_t qh[2][2][4], ql[2][2][4];                  // Q tiles as A fragments (fp16 hi / lo), 2 k16 steps
+    // ---------------------------------------------------------------- (b) K_h, V_h of every 16-frame tile (rotary on k)
+    for (int tile = warp; tile < ntiles; tile += NWARP) {
+      const int f0 = tile * 16, fr0 = f0 + g, fr1 = f0 + g + 8;
+      float acc[4][4];
+      project(f0, 1, acc);
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const int tile = warp + 8 * b;
-      if (tile >= ntiles) continue;
-      const int f0 = tile * 16;
-      // A fragments of x for the 4 k16 steps (hi and lo)
-      uint32_t xa_h[4][4], xa_l[4][4];
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const __half* r0p = Xh + (f0 + g) * X_LD + ks * 16 + 2 * t;
-        const __half* r0l = Xl + (f0 + g) * X_LD + ks * 16 + 2 * t;
-        xa_h[ks][0] = lds32(r0p); xa_h[ks][1] = lds32(r0p + 8 * X_LD); xa_h[ks][2] = lds32(r0p + 8); xa_h[ks][3] = lds32(r0p + 8 * X_LD + 8);
-        xa_l[ks][0] = lds32(r0l); xa_l[ks][1] = lds32(r0l + 8 * X_LD); xa_l[ks][2] = lds32(r0l + 8); xa_l[ks][3] = lds32(r0l + 8 * X_LD + 8);
+      for (int n = 0; n < 4; ++n) {
+        uint32_t h0, l0, h1, l1;
+        split2h(acc[n][0], acc[n][1], h0, l0); split2h(acc[n][2], acc[n][3], h1, l1);
+        *reinterpret_cast<uint32_t*>(&Kh[fr0 * K_LD + n * 8 + 2 * t]) = h0;
+        *reinterpret_cast<uint32_t*>(&Kl[fr0 * K_LD + n * 8 + 2 * t]) = l0;
+        *reinterpret_cast<uint32_t*>(&Kh[fr1 * K_LD + n * 8 + 2 * t]) = h1;
+        *reinterpret_cast<uint32_t*>(&Kl[fr1 * K_LD + n * 8 + 2 * t]) = l1;
       }
-      const float mu0 = s_stat[2 * (f0 + g)], rs0 = s_stat[2 * (f0 + g) + 1];
-      const float mu1 = s_stat[2 * (f0 + g + 8)], rs1 = s_stat[2 * (f0 + g + 8) + 1];
-      const int fr0 = f0 + g, fr1 = f0 + g + 8;         // frame (= rotary position index into a.rot) of rows g / g+8
-#pragma unroll
-      for (int part = 2; part >= 0; --part) {           // 2: v, 1: k, 0: q  (q last: its fragments stay live)
-        float acc[4][4];
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) acc[n][c] = 0.f;
-          const int wrow = part * 32 + n * 8 + g;       // row of W'_h = output column
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const int off = wrow * W_LD + ks * 16 + 2 * t;
-            const uint32_t bh0 = lds32(Wh + off), bh1 = lds32(Wh + off + 8);
-            const uint32_t bl0 = lds32(Wl + off), bl1 = lds32(Wl + off + 8);
-            mma16816(acc[n], xa_l[ks], bh0, bh1);
-            mma16816(acc[n], xa_h[ks], bl0, bl1);
-            mma16816(acc[n], xa_h[ks], bh0, bh1);
-          }
-          // LayerNorm fold + weight pre-scale:  rstd * (acc / wscale - mu * colsum)
-          const float w0 = __ldg(wsum + part * 256 + n * 8 + 2 * t), w1 = __ldg(wsum + part * 256 + n * 8 + 2 * t + 1);
-          acc[n][0] = rs0 * (acc[n][0] * a.inv_wscale - mu0 * w0);
-          acc[n][1] = rs0 * (acc[n][1] * a.inv_wscale - mu0 * w1);
-          acc[n][2] = rs1 * (acc[n][2] * a.inv_wscale - mu1 * w0);
-          acc[n][3] = rs1 * (acc[n][3] * a.inv_wscale - mu1 * w1);
-          if (part < 2) {                                // rotary on q and k: interleaved pair (2i, 2i+1), pair index = n*4 + t
-            const float2 cs0 = *reinterpret_cast<const float2*>(a.rot + ((size_t)min(fr0, F - 1) * 16 + n * 4 + t) * 2);
-            const float2 cs1 = *reinterpret_cast<const float2*>(a.rot + ((size_t)min(fr1, F - 1) * 16 + n * 4 + t) * 2);
-            const float x0 = acc[n][0], x1 = acc[n][1], x2 = acc[n][2], x3 = acc[n][3];
-            acc[n][0] = x0 * cs0.x - x1 * cs0.y; acc[n][1] = x1 * cs0.x + x0 * cs0.y;
-            acc[n][2] = x2 * cs1.x - x3 * cs1.y; acc[n][3] = x3 * cs1.x + x2 * cs1.y;
-          }
-        }
-        if (part == 1) {                                 // K rows (row-major, fp16 hi/lo)
-#pragma unroll
-          for (int n = 0; n < 4; ++n) {
-            uint32_t h0, l0, h1, l1;
-            split2h(acc[n][0], acc[n][1], h0, l0); split2h(acc[n][2], acc[n][3], h1, l1);
-            *reinterpret_cast<uint32_t*>(&Kh[fr0 * K_LD + n * 8 + 2 * t]) = h0;
-            *reinterpret_cast<uint32_t*>(&Kl[fr0 * K_LD + n * 8 + 2 * t]) = l0;
-            *reinterpret_cast<uint32_t*>(&Kh[fr1 * K_LD + n * 8 + 2 * t]) = h1;
-            *reinterpret_cast<uint32_t*>(&Kl[fr1 * K_LD + n * 8 + 2 * t]) = l1;
-          }
-        } else if (part == 2) {                          // V transposed: Vt[d][frame]
-#pragma unroll
-          for (int n = 0; n < 4; ++n)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              __half hh, ll;
-              split1h(acc[n][c], hh, ll);
-              const int d = n * 8 + 2 * t + (c & 1), fr = (c & 2) ? fr1 : fr0;
-              Vh[d * v_ld + fr] = hh; Vl[d * v_ld + fr] = ll;
-            }
-        } else {                                         // Q: accumulator tiles (2ks, 2ks+1) == A fragment of k16 step ks
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            split2h(acc[2 * ks][0], acc[2 * ks][1], qh[b][ks][0], ql[b][ks][0]);
-            split2h(acc[2 * ks][2], acc[2 * ks][3], qh[b][ks][1], ql[b][ks][1]);
-            split2h(acc[2 * ks + 1][0], acc[2 * ks + 1][1], qh[b][ks][2], ql[b][ks][2]);
-            split2h(acc[2 * ks + 1][2], acc[2 * ks + 1][3], qh[b][ks][3], ql[b][ks][3]);
-          }
-        }
-      }
-    }
-    __syncthreads();                                    // K_h, V_h^T of every frame are in shared memory
-
-    // ---------------------------------------------------------------- (e) banded attention + (f) out-projection per own tile
-    const float* bias = s_bias + head * nbias + band;
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const int tile = warp + 8 * b;
-      if (tile >= ntiles) continue;
-      const int i0 = tile * 16;
-      if (i0 >= a.q_hi || i0 + 16 <= a.q_lo) continue;  // tile holds no frame whose output is needed (halo tile)
-      float o[4][4], mrow[2] = {-1e30f, -1e30f}, lrow[2] = {0.f, 0.f};
+      project(f0, 2, acc);
 #pragma unroll
       for (int n = 0; n < 4; ++n)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) o[n][c] = 0.f;
-      const int kr_lo = max(0, i0 - band), kr_hi = min(F, i0 + 16 + band);
-      for (int kr0 = kr_lo; kr0 < kr_hi; kr0 += 32) {
-        float s[4][4];
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) s[n][c] = 0.f;
-          const int krow = kr0 + n * 8 + g;
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const int off = krow * K_LD + ks * 16 + 2 * t;
-            const uint32_t bh0 = lds32(Kh + off), bh1 = lds32(Kh + off + 8);
-            const uint32_t bl0 = lds32(Kl + off), bl1 = lds32(Kl + off + 8);
-            mma16816(s[n], ql[b][ks], bh0, bh1);
-            mma16816(s[n], qh[b][ks], bl0, bl1);
-            mma16816(s[n], qh[b][ks], bh0, bh1);
-          }
+        for (int c = 0; c < 4; ++c) {                     // V transposed: Vt[d][frame]
+          __half hh, ll;
+          split1h(acc[n][c], hh, ll);
+          const int d = n * 8 + 2 * t + (c & 1), fr = (c & 2) ? fr1 : fr0;
+          Vh[d * v_ld + fr] = hh; Vl[d * v_ld + fr] = ll;
         }
-        float mnew[2] = {mrow[0], mrow[1]};
-        bool ok[4][4];
+    }
+    // ---------------------------------------------------------------- (c) Q_h of the owned query tile -> A fragments in registers
+    uint32_t qh[2][4], ql[2][4];
+    if (has_q) {
+      float acc[4][4];
+      project(qtile * 16, 0, acc);
 #pragma unroll
-        for (int n = 0; n < 4; ++n)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int i = i0 + g + ((c & 2) ? 8 : 0);
-            const int j = kr0 + n * 8 + 2 * t + (c & 1);
-            const int rel = j - i;
-            const bool v = ((unsigned)(rel + band) <= (unsigned)(2 * band)) && (j < F);
-            ok[n][c] = v;
-            if (v) { s[n][c] += bias[rel]; mnew[c >> 1] = fmaxf(mnew[c >> 1], s[n][c]); }
-          }
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 1));
-          mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 2));
-        }
-        const float corr0 = __expf(mrow[0] - mnew[0]), corr1 = __expf(mrow[1] - mnew[1]);
-        mrow[0] = mnew[0]; mrow[1] = mnew[1];
-        float ps0 = 0.f, ps1 = 0.f;
-#pragma unroll
-        for (int n = 0; n < 4; ++n)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float pv = ok[n][c] ? __expf(s[n][c] - mnew[c >> 1]) : 0.f;
-            s[n][c] = pv;
-            if (c & 2) ps1 += pv; else ps0 += pv;
-          }
-        lrow[0] = lrow[0] * corr0 + ps0;
-        lrow[1] = lrow[1] * corr1 + ps1;
-        uint32_t ph[2][4], pl[2][4];
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          split2h(s[2 * ks][0], s[2 * ks][1], ph[ks][0], pl[ks][0]);
-          split2h(s[2 * ks][2], s[2 * ks][3], ph[ks][1], pl[ks][1]);
-          split2h(s[2 * ks + 1][0], s[2 * ks + 1][1], ph[ks][2], pl[ks][2]);
-          split2h(s[2 * ks + 1][2], s[2 * ks + 1][3], ph[ks][3], pl[ks][3]);
-        }
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
-          const int drow = (n * 8 + g) * v_ld;
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const int off = drow + kr0 + ks * 16 + 2 * t;
-            const uint32_t bh0 = lds32(Vh + off), bh1 = lds32(Vh + off + 8);
-            const uint32_t bl0 = lds32(Vl + off), bl1 = lds32(Vl + off + 8);
-            mma16816(acc, pl[ks], bh0, bh1);
-            mma16816(acc, ph[ks], bl0, bl1);
-            mma16816(acc, ph[ks], bh0, bh1);
-          }
-          o[n][0] = o[n][0] * corr0 + acc[0]; o[n][1] = o[n][1] * corr0 + acc[1];
-          o[n][2] = o[n][2] * corr1 + acc[2]; o[n][3] = o[n][3] * corr1 + acc[3];
-        }
+      for (int ks = 0; ks < 2; ++ks) {                    // accumulator tiles (2ks, 2ks+1) == A fragment of k16 step ks
+        split2h(acc[2 * ks][0], acc[2 * ks][1], qh[ks][0], ql[ks][0]);
+        split2h(acc[2 * ks][2], acc[2 * ks][3], qh[ks][1], ql[ks][1]);
+        split2h(acc[2 * ks + 1][0], acc[2 * ks + 1][1], qh[ks][2], ql[ks][2]);
+        split2h(acc[2 * ks + 1][2], acc[2 * ks + 1][3], qh[ks][3], ql[ks][3]);
       }
-      // normalise
-      float l0 = lrow[0], l1 = lrow[1];
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-      const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-      // (f) y_tile += O_h (16 x 32) * Wout_h^T (32 x 64): O's accumulator tiles (2ks, 2ks+1) == A fragment of k16 step ks
-      uint32_t oh[2][4], ol[2][4];
+    }
+    __syncthreads();                                    // K_h, V_h^T of every frame are in shared memory
+    if (!has_q) continue;
+
+    // ---------------------------------------------------------------- (d) banded attention of the query tile
+    const float* bias = s_bias + head * nbias + band;
+    const int i0 = qtile * 16;
+    float o[4][4], mrow[2] = {-1e30f, -1e30f}, lrow[2] = {0.f, 0.f};
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[n][c] = 0.f;
+    const int kr_lo = max(0, i0 - band) & ~7, kr_hi = min(F, i0 + 16 + band);
+    for (int kr0 = kr_lo; kr0 < kr_hi; kr0 += 32) {
+      float s[4][4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[n][c] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          uint32_t b[4];
+          ldsm4(b, ((lm & 2) ? Kl : Kh) + (kr0 + n * 8 + lr) * K_LD + ks * 16 + (lm & 1) * 8);
+          mma3(s[n], qh[ks], ql[ks], b);
+        }
+      // mask (band, sequence end) + relative position bias; every real row has a valid key in its first block, so a masked
+      // score of -1e30 always meets a finite running maximum
+      float mnew[2] = {mrow[0], mrow[1]};
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int i = i0 + g + ((c & 2) ? 8 : 0);
+          const int j = kr0 + n * 8 + 2 * t + (c & 1);
+          const int rel = j - i;
+          const bool v = ((unsigned)(rel + band) <= (unsigned)(2 * band)) && (j < F);
+          s[n][c] = v ? s[n][c] + bias[v ? rel : 0] : -1e30f;
+          mnew[c >> 1] = fmaxf(mnew[c >> 1], s[n][c]);
+        }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 1));
+        mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 2));
+      }
+      const float corr0 = __expf(mrow[0] - mnew[0]), corr1 = __expf(mrow[1] - mnew[1]);
+      mrow[0] = mnew[0]; mrow[1] = mnew[1];
+      float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        s[n][0] = __expf(s[n][0] - mnew[0]); s[n][1] = __expf(s[n][1] - mnew[0]);
+        s[n][2] = __expf(s[n][2] - mnew[1]); s[n][3] = __expf(s[n][3] - mnew[1]);
+        ps0 += s[n][0] + s[n][1]; ps1 += s[n][2] + s[n][3];
+      }
+      lrow[0] = lrow[0] * corr0 + ps0;
+      lrow[1] = lrow[1] * corr1 + ps1;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) { o[n][0] *= corr0; o[n][1] *= corr0; o[n][2] *= corr1; o[n][3] *= corr1; }
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
-        split2h(o[2 * ks][0] * inv0, o[2 * ks][1] * inv0, oh[ks][0], ol[ks][0]);
-        split2h(o[2 * ks][2] * inv1, o[2 * ks][3] * inv1, oh[ks][1], ol[ks][1]);
-        split2h(o[2 * ks + 1][0] * inv0, o[2 * ks + 1][1] * inv0, oh[ks][2], ol[ks][2]);
-        split2h(o[2 * ks + 1][2] * inv1, o[2 * ks + 1][3] * inv1, oh[ks][3], ol[ks][3]);
-      }
+        uint32_t ph[4], pl[4];                            // P's accumulator tiles (2ks, 2ks+1) == A fragment of k16 step ks
+        split2h(s[2 * ks][0], s[2 * ks][1], ph[0], pl[0]);
+        split2h(s[2 * ks][2], s[2 * ks][3], ph[1], pl[1]);
+        split2h(s[2 * ks + 1][0], s[2 * ks + 1][1], ph[2], pl[2]);
+        split2h(s[2 * ks + 1][2], s[2 * ks + 1][3], ph[3], pl[3]);
 #pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        const int wrow = (n * 8 + g) * WO_LD;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const int off = wrow + ks * 16 + 2 * t;
-          const uint32_t bh0 = lds32(Oh + off), bh1 = lds32(Oh + off + 8);
-          const uint32_t bl0 = lds32(Ol + off), bl1 = lds32(Ol + off + 8);
-          mma16816(acc, ol[ks], bh0, bh1);
-          mma16816(acc, oh[ks], bl0, bl1);
-          mma16816(acc, oh[ks], bh0, bh1);
+        for (int n = 0; n < 4; ++n) {
+          uint32_t b[4];
+          ldsm4(b, ((lm & 2) ? Vl : Vh) + (n * 8 + lr) * v_ld + kr0 + ks * 16 + (lm & 1) * 8);
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};            // RN accumulation across key blocks outside the tensor core
+          mma3(acc, ph, pl, b);
+          o[n][0] += acc[0]; o[n][1] += acc[1]; o[n][2] += acc[2]; o[n][3] += acc[3];
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) y[b][n][c] += acc[c] * a.inv_oscale;     // RN accumulation over heads outside the tensor core
       }
+    }
+    float l0 = lrow[0], l1 = lrow[1];
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    // ---------------------------------------------------------------- (e) y_tile += O_h (16 x 32) * Wout_h^T (32 x 64)
+    uint32_t oh[2][4], ol[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      split2h(o[2 * ks][0] * inv0, o[2 * ks][1] * inv0, oh[ks][0], ol[ks][0]);
+      split2h(o[2 * ks][2] * inv1, o[2 * ks][3] * inv1, oh[ks][1], ol[ks][1]);
+      split2h(o[2 * ks + 1][0] * inv0, o[2 * ks + 1][1] * inv0, oh[ks][2], ol[ks][2]);
+      split2h(o[2 * ks + 1][2] * inv1, o[2 * ks + 1][3] * inv1, oh[ks][3], ol[ks][3]);
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t b[4];
+        ldsm4(b, ((lm & 2) ? Ol : Oh) + (n * 8 + lr) * WO_LD + ks * 16 + (lm & 1) * 8);
+        mma3(acc, oh[ks], ol[ks], b);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) y[n][c] += acc[c] * a.inv_oscale;           // RN accumulation over heads outside the tensor core
     }
   }
 
   // ------------------------------------------------------------------ out = residual + y for the frames this call owns
-#pragma unroll
-  for (int b = 0; b < 2; ++b) {
-    const int tile = warp + 8 * b;
-    if (tile >= ntiles) continue;
+  if (has_q) {
 #pragma unroll
     for (int hrow = 0; hrow < 2; ++hrow) {
-      const int f = tile * 16 + g + 8 * hrow;
+      const int f = qtile * 16 + g + 8 * hrow;
       if (f < a.q_lo || f >= a.q_hi) continue;
       const size_t orow = (size_t)(f - a.q_lo) * a.P + pix;
       const float* res = a.res + orow * a.ldr;
@@ -362,7 +344,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_fused_kernel(TemporalFusedArg
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
         const float2 r = *reinterpret_cast<const float2*>(res + n * 8 + 2 * t);
-        *reinterpret_cast<float2*>(dst + n * 8 + 2 * t) = make_float2(r.x + y[b][n][2 * hrow], r.y + y[b][n][2 * hrow + 1]);
+        *reinterpret_cast<float2*>(dst + n * 8 + 2 * t) = make_float2(r.x + y[n][2 * hrow], r.y + y[n][2 * hrow + 1]);
       }
     }
   }
@@ -376,14 +358,14 @@ size_t smem_bytes(int F, int band) {
 
 }  // namespace
 
-bool temporal_fused_supported(int C_, int F, int band) {
-  if (C_ != C || band > 40 || F < 1) return false;
-  if (((F + 15) >> 4) > 16) return false;                       // 8 warps x 2 tiles of 16 frames
+bool temporal_fused_supported(int C_, int F, int band, int q_lo, int q_hi) {
+  if (C_ != C || band < 1 || band > 64 || F < 1 || q_lo < 0 || q_hi > F || q_lo >= q_hi) return false;
+  if (((q_hi + 15) >> 4) - (q_lo >> 4) > NWARP) return false;   // one 16-frame query tile per warp
   return smem_bytes(F, band) <= 225 * 1024;
 }
 
 int launch_temporal_fused(const TemporalFusedArgs& a, cudaStream_t st) {
-  if (!temporal_fused_supported(C, a.F, a.band)) { set_last_error("temporal_fused: unsupported shape"); return -1; }
+  if (!temporal_fused_supported(C, a.F, a.band, a.q_lo, a.q_hi)) { set_last_error("temporal_fused: unsupported shape"); return -1; }
   static size_t attr_bytes = 0;
   const size_t smem = smem_bytes(a.F, a.band);
   if (smem > attr_bytes) {

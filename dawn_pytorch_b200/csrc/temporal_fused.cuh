@@ -22,7 +22,7 @@ struct TemporalFusedArgs {
   float inv_wscale, inv_oscale;
 };
 
-bool temporal_fused_supported(int C, int F, int band);
+bool temporal_fused_supported(int C, int F, int band, int q_lo, int q_hi);
 int launch_temporal_fused(const TemporalFusedArgs& a, cudaStream_t st);
 void temporal_fused_pack(const float* wqkv, const float* wout, std::vector<uint16_t>& Wq, std::vector<uint16_t>& Wo, float* inv_wscale,
                          float* inv_oscale);

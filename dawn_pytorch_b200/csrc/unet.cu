@@ -619,7 +619,7 @@ int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const st
     DAWN_NCCL_OK(g_nccl.GroupEnd());
     xe = Act{h->XE, x.C, x.C, x.H, x.W};
   }
-  if (h->use_fused_ta && w.fq && temporal_fused_supported(x.C, Fe, h->cfg.win_width)) {
+  if (h->use_fused_ta && w.fq && temporal_fused_supported(x.C, Fe, h->cfg.win_width, hl, hl + F)) {
     TemporalFusedArgs a{};
     a.x = xe.p; a.ldx = xe.ld; a.res = x.p; a.ldr = x.ld; a.out = dst.p; a.ldo = dst.ld;
     a.F = Fe; a.P = P; a.q_lo = hl; a.q_hi = hl + F;
