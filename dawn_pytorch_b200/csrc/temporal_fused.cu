@@ -31,6 +31,8 @@ constexpr int K_LD = 40;              // halfs per K row
 constexpr int WO_LD = 40;             // halfs per Wout_h row ([n = channel][k = head dim])
 constexpr int NTH = 512;
 constexpr int NWARP = NTH / 32;
+constexpr int W_STAGE = 2 * 96 * W_LD + 2 * 64 * WO_LD;      // halfs per weight stage
+constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -44,18 +46,30 @@ __device__ __forceinline__ void ldsm4(uint32_t (&r)[4], const __half* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
+__device__ __forceinline__ void ldsm4_trans(uint32_t (&r)[4], const __half* p) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+// x = hi + lo with hi the leading 11 significant bits (truncated, exact in fp16) and lo the fp16-rounded remainder
 __device__ __forceinline__ void split2h(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  const float h0 = __uint_as_float((__float_as_uint(x0) + 0x1000u) & 0xFFFFE000u);
-  const float h1 = __uint_as_float((__float_as_uint(x1) + 0x1000u) & 0xFFFFE000u);
+  const float h0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
+  const float h1 = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
   const __half2 h = __floats2half2_rn(h0, h1);
   const __half2 l = __floats2half2_rn(x0 - h0, x1 - h1);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-__device__ __forceinline__ void split1h(float x, __half& hi, __half& lo) {
-  const float h = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-  hi = __float2half_rn(h);
-  lo = __float2half_rn(x - h);
 }
 // 3-term split product: acc += a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, b = {hi k0-7, hi k8-15, lo k0-7, lo k8-15}
 __device__ __forceinline__ void mma3(float (&acc)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const uint32_t (&b)[4]) {
@@ -69,19 +83,16 @@ __global__ void __launch_bounds__(NTH, 1) temporal_fused_kernel(TemporalFusedArg
   const int F = a.F;                                   // sequence length held on chip (incl. halo frames when sharded)
   const int Fp = (F + 15) & ~15;                       // padded to whole 16-frame tiles
   const int KROWS = Fp + 32;                           // key rows incl. zero rows read by the last 32-key block
-  const int v_ld = KROWS + 8;
+  const int nbuf = a.nbuf;                             // weight stages: 2 = next head's weights stream in behind the attention
   __half* Xh = reinterpret_cast<__half*>(tf_smem);
   __half* Xl = Xh + Fp * X_LD;
-  __half* Wh = Xl + Fp * X_LD;
-  __half* Wl = Wh + 96 * W_LD;
-  __half* Kh = Wl + 96 * W_LD;
+  __half* Kh = Xl + Fp * X_LD;
   __half* Kl = Kh + KROWS * K_LD;
-  __half* Vh = Kl + KROWS * K_LD;
-  __half* Vl = Vh + 32 * v_ld;
-  __half* Oh = Vl + 32 * v_ld;                         // Wout_h hi: [64][WO_LD]
-  __half* Ol = Oh + 64 * WO_LD;
-  float* s_stat = reinterpret_cast<float*>(Ol + 64 * WO_LD);      // [Fp][2]  (mu, rstd)
-  float* s_bias = s_stat + 2 * Fp;                                 // [8][2*band+1]
+  __half* Vh = Kl + KROWS * K_LD;                      // V_h row-major like K_h (B operand of P*V through ldmatrix.trans)
+  __half* Vl = Vh + KROWS * K_LD;
+  __half* Wst = Vl + KROWS * K_LD;                     // weight stages: [W'_h hi | lo : 2 x 96 x W_LD][Wout_h hi | lo : 2 x 64 x WO_LD]
+  float* s_stat = reinterpret_cast<float*>(Wst + nbuf * W_STAGE);  // [Fp][2]  (mu, rstd)
+  float* s_bias = s_stat + 2 * Fp;                                 // [8][2*band+1], pre-multiplied by log2(e)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -91,7 +102,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_fused_kernel(TemporalFusedArg
   const int nbias = 2 * band + 1;
 
   // ------------------------------------------------------------------ phase 0: x rows of this pixel, LN statistics, fp16 split
-  for (int i = tid; i < 8 * nbias; i += NTH) s_bias[i] = a.bias[i];
+  for (int i = tid; i < 8 * nbias; i += NTH) s_bias[i] = a.bias[i] * LOG2E;
   {
     const int l16 = tid & 15;                           // 16 lanes x float4 = one 64-channel row
     for (int f0 = 0; f0 < Fp; f0 += NTH / 16) {
@@ -115,10 +126,9 @@ __global__ void __launch_bounds__(NTH, 1) temporal_fused_kernel(TemporalFusedArg
       }
     }
     // zero the key rows / value columns beyond the sequence once (masked lanes must multiply finite numbers)
-    for (int i = tid; i < (KROWS - F) * K_LD; i += NTH) { Kh[F * K_LD + i] = __float2half(0.f); Kl[F * K_LD + i] = __float2half(0.f); }
-    for (int i = tid; i < 32 * (v_ld - F); i += NTH) {
-      const int d = i / (v_ld - F), c = F + i % (v_ld - F);
-      Vh[d * v_ld + c] = __float2half(0.f); Vl[d * v_ld + c] = __float2half(0.f);
+    for (int i = tid; i < (KROWS - F) * K_LD; i += NTH) {
+      Kh[F * K_LD + i] = __float2half(0.f); Kl[F * K_LD + i] = __float2half(0.f);
+      Vh[F * K_LD + i] = __float2half(0.f); Vl[F * K_LD + i] = __float2half(0.f);
     }
   }
 
@@ -134,6 +144,22 @@ __global__ void __launch_bounds__(NTH, 1) temporal_fused_kernel(TemporalFusedArg
   // One projection part (0: q, 1: k, 2: v) of one 16-frame tile: acc = x_tile (16 x 64) * W'_h[part]^T (64 x 32), LayerNorm folded,
   // rotary applied to q and k.  Four independent accumulator chains (n-tiles) per k16 step.
   int head_off = 0;                                     // head * 32: column offset inside the q | k | v blocks of wsum
+  const __half* Wh = Wst;                               // current stage (set per head)
+  // stream one head's weights into a stage (fp16 hi | lo images, dense in global, padded rows in shared memory)
+  auto stage_weights = [&](int head, __half* dst) {
+    const uint4* src = reinterpret_cast<const uint4*>(a.Wqkv + (size_t)head * 2 * 96 * C);       // hi then lo, dense [96][64]
+    for (int i = tid; i < 2 * 96 * C / 8; i += NTH) {
+      const int r = i / (C / 8), c8 = i - r * (C / 8);                                             // r in [0, 192): hi rows then lo rows
+      cp_async_16(dst + r * W_LD + c8 * 8, src + i);
+    }
+    const uint4* so = reinterpret_cast<const uint4*>(a.Wout + (size_t)head * 2 * 64 * 32);        // hi then lo, dense [64][32]
+    __half* od = dst + 2 * 96 * W_LD;
+    for (int i = tid; i < 2 * 64 * 32 / 8; i += NTH) {
+      const int r = i >> 2, c8 = i & 3;                                                            // r in [0, 128)
+      cp_async_16(od + r * WO_LD + c8 * 8, so + i);
+    }
+    cp_async_commit();
+  };
   auto project = [&](int f0, int part, float (&acc)[4][4]) {
 #pragma unroll
     for (int n = 0; n < 4; ++n)
@@ -148,7 +174,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_fused_kernel(TemporalFusedArg
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
         uint32_t b[4];
-        ldsm4(b, ((lm & 2) ? Wl : Wh) + (part * 32 + n * 8 + lr) * W_LD + ks * 16 + (lm & 1) * 8);
+        ldsm4(b, Wh + ((lm >> 1) * 96 + part * 32 + n * 8 + lr) * W_LD + ks * 16 + (lm & 1) * 8);
         mma3(acc[n], ah, al, b);
       }
     }
@@ -172,24 +198,20 @@ __global__ void __launch_bounds__(NTH, 1) temporal_fused_kernel(TemporalFusedArg
     }
   };
 
+  if (nbuf == 2) stage_weights(0, Wst);
   for (int head = 0; head < 8; ++head) {
-    __syncthreads();                                    // previous head's K/V/W no longer needed (also orders phase 0)
-    // ---------------------------------------------------------------- (a) this head's weights: W'_h [96][64], Wout_h [64][32] (fp16 hi | lo)
-    {
-      const uint4* src = reinterpret_cast<const uint4*>(a.Wqkv + (size_t)head * 2 * 96 * C);     // hi then lo, dense [96][64]
-      for (int i = tid; i < 2 * 96 * C / 8; i += NTH) {
-        const int part = i / (96 * C / 8), j = i - part * (96 * C / 8);
-        const int r = j / (C / 8), c8 = j - r * (C / 8);
-        *reinterpret_cast<uint4*>((part ? Wl : Wh) + r * W_LD + c8 * 8) = __ldg(src + i);
-      }
-      const uint4* so = reinterpret_cast<const uint4*>(a.Wout + (size_t)head * 2 * 64 * 32);      // hi then lo, dense [64][32]
-      for (int i = tid; i < 2 * 64 * 32 / 8; i += NTH) {
-        const int part = i / (64 * 32 / 8), j = i - part * (64 * 32 / 8);
-        const int r = j >> 2, c8 = j & 3;
-        *reinterpret_cast<uint4*>((part ? Ol : Oh) + r * WO_LD + c8 * 8) = __ldg(so + i);
-      }
+    if (nbuf == 2) {
+      cp_async_wait_all();
+      __syncthreads();                                  // this head's weights landed; previous head's K/V and other stage are free
+      Wh = Wst + (head & 1) * W_STAGE;
+      if (head + 1 < 8) stage_weights(head + 1, Wst + ((head + 1) & 1) * W_STAGE);
+    } else {
+      __syncthreads();
+      stage_weights(head, Wst);
+      cp_async_wait_all();
+      __syncthreads();
     }
-    __syncthreads();
+    const __half* Oh = Wh + 2 * 96 * W_LD;              // Wout_h: hi rows [0, 64), lo rows [64, 128)
     head_off = head * 32;
 
     // ---------------------------------------------------------------- (b) K_h, V_h of every 16-frame tile (rotary on k)
@@ -208,20 +230,24 @@ __global__ void __launch_bounds__(NTH, 1) temporal_fused_kernel(TemporalFusedArg
       }
       project(f0, 2, acc);
 #pragma unroll
-      for (int n = 0; n < 4; ++n)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {                     // V transposed: Vt[d][frame]
-          __half hh, ll;
-          split1h(acc[n][c], hh, ll);
-          const int d = n * 8 + 2 * t + (c & 1), fr = (c & 2) ? fr1 : fr0;
-          Vh[d * v_ld + fr] = hh; Vl[d * v_ld + fr] = ll;
-        }
+      for (int n = 0; n < 4; ++n) {
+        uint32_t h0, l0, h1, l1;
+        split2h(acc[n][0], acc[n][1], h0, l0); split2h(acc[n][2], acc[n][3], h1, l1);
+        *reinterpret_cast<uint32_t*>(&Vh[fr0 * K_LD + n * 8 + 2 * t]) = h0;
+        *reinterpret_cast<uint32_t*>(&Vl[fr0 * K_LD + n * 8 + 2 * t]) = l0;
+        *reinterpret_cast<uint32_t*>(&Vh[fr1 * K_LD + n * 8 + 2 * t]) = h1;
+        *reinterpret_cast<uint32_t*>(&Vl[fr1 * K_LD + n * 8 + 2 * t]) = l1;
+      }
     }
     // ---------------------------------------------------------------- (c) Q_h of the owned query tile -> A fragments in registers
     uint32_t qh[2][4], ql[2][4];
     if (has_q) {
       float acc[4][4];
       project(qtile * 16, 0, acc);
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[n][c] *= LOG2E;   // scores live in the log2 domain: softmax through ex2
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {                    // accumulator tiles (2ks, 2ks+1) == A fragment of k16 step ks
         split2h(acc[2 * ks][0], acc[2 * ks][1], qh[ks][0], ql[ks][0]);
@@ -256,32 +282,42 @@ __global__ void __launch_bounds__(NTH, 1) temporal_fused_kernel(TemporalFusedArg
           ldsm4(b, ((lm & 2) ? Kl : Kh) + (kr0 + n * 8 + lr) * K_LD + ks * 16 + (lm & 1) * 8);
           mma3(s[n], qh[ks], ql[ks], b);
         }
-      // mask (band, sequence end) + relative position bias; every real row has a valid key in its first block, so a masked
-      // score of -1e30 always meets a finite running maximum
+      // relative position bias (+ band / sequence-end mask on the edge blocks only); every real row has a valid key in its first
+      // block, so a masked score of -1e30 always meets a finite running maximum
       float mnew[2] = {mrow[0], mrow[1]};
+      const int rel0 = kr0 - i0 + 2 * t - g;             // rel of element (n = 0, c = 0)
+      const bool edge = (kr0 + 31 - i0 > band) || (kr0 - i0 - 15 < -band) || (kr0 + 32 > F);
+      if (edge) {
 #pragma unroll
-      for (int n = 0; n < 4; ++n)
+        for (int n = 0; n < 4; ++n)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int i = i0 + g + ((c & 2) ? 8 : 0);
-          const int j = kr0 + n * 8 + 2 * t + (c & 1);
-          const int rel = j - i;
-          const bool v = ((unsigned)(rel + band) <= (unsigned)(2 * band)) && (j < F);
-          s[n][c] = v ? s[n][c] + bias[v ? rel : 0] : -1e30f;
-          mnew[c >> 1] = fmaxf(mnew[c >> 1], s[n][c]);
-        }
+          for (int c = 0; c < 4; ++c) {
+            const int rel = rel0 + n * 8 + (c & 1) - ((c & 2) ? 8 : 0);
+            const bool v = ((unsigned)(rel + band) <= (unsigned)(2 * band)) && (kr0 + n * 8 + 2 * t + (c & 1) < F);
+            s[n][c] = v ? s[n][c] + bias[v ? rel : 0] : -1e30f;
+            mnew[c >> 1] = fmaxf(mnew[c >> 1], s[n][c]);
+          }
+      } else {
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            s[n][c] += bias[rel0 + n * 8 + (c & 1) - ((c & 2) ? 8 : 0)];
+            mnew[c >> 1] = fmaxf(mnew[c >> 1], s[n][c]);
+          }
+      }
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 1));
         mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 2));
       }
-      const float corr0 = __expf(mrow[0] - mnew[0]), corr1 = __expf(mrow[1] - mnew[1]);
+      const float corr0 = ex2(mrow[0] - mnew[0]), corr1 = ex2(mrow[1] - mnew[1]);
       mrow[0] = mnew[0]; mrow[1] = mnew[1];
       float ps0 = 0.f, ps1 = 0.f;
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
-        s[n][0] = __expf(s[n][0] - mnew[0]); s[n][1] = __expf(s[n][1] - mnew[0]);
-        s[n][2] = __expf(s[n][2] - mnew[1]); s[n][3] = __expf(s[n][3] - mnew[1]);
+        s[n][0] = ex2(s[n][0] - mnew[0]); s[n][1] = ex2(s[n][1] - mnew[0]);
+        s[n][2] = ex2(s[n][2] - mnew[1]); s[n][3] = ex2(s[n][3] - mnew[1]);
         ps0 += s[n][0] + s[n][1]; ps1 += s[n][2] + s[n][3];
       }
       lrow[0] = lrow[0] * corr0 + ps0;
@@ -298,7 +334,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_fused_kernel(TemporalFusedArg
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
           uint32_t b[4];
-          ldsm4(b, ((lm & 2) ? Vl : Vh) + (n * 8 + lr) * v_ld + kr0 + ks * 16 + (lm & 1) * 8);
+          ldsm4_trans(b, ((lm & 2) ? Vl : Vh) + (kr0 + ks * 16 + (lm & 1) * 8 + lr) * K_LD + n * 8);
           float acc[4] = {0.f, 0.f, 0.f, 0.f};            // RN accumulation across key blocks outside the tensor core
           mma3(acc, ph, pl, b);
           o[n][0] += acc[0]; o[n][1] += acc[1]; o[n][2] += acc[2]; o[n][3] += acc[3];
@@ -324,7 +360,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_fused_kernel(TemporalFusedArg
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         uint32_t b[4];
-        ldsm4(b, ((lm & 2) ? Ol : Oh) + (n * 8 + lr) * WO_LD + ks * 16 + (lm & 1) * 8);
+        ldsm4(b, Oh + ((lm >> 1) * 64 + n * 8 + lr) * WO_LD + ks * 16 + (lm & 1) * 8);
         mma3(acc, oh[ks], ol[ks], b);
       }
 #pragma unroll
@@ -350,24 +386,27 @@ __global__ void __launch_bounds__(NTH, 1) temporal_fused_kernel(TemporalFusedArg
   }
 }
 
-size_t smem_bytes(int F, int band) {
-  const int Fp = (F + 15) & ~15, KROWS = Fp + 32, v_ld = KROWS + 8;
-  size_t halfs = (size_t)2 * Fp * X_LD + 2 * 96 * W_LD + 2 * KROWS * K_LD + 2 * 32 * v_ld + 2 * 64 * WO_LD;
+size_t smem_bytes(int F, int band, int nbuf) {
+  const int Fp = (F + 15) & ~15, KROWS = Fp + 32;
+  size_t halfs = (size_t)2 * Fp * X_LD + 4 * KROWS * K_LD + (size_t)nbuf * W_STAGE;
   return halfs * 2 + (size_t)(2 * Fp + 8 * (2 * band + 1)) * 4;
 }
+constexpr size_t kSmemMax = 225 * 1024;
 
 }  // namespace
 
 bool temporal_fused_supported(int C_, int F, int band, int q_lo, int q_hi) {
   if (C_ != C || band < 1 || band > 64 || F < 1 || q_lo < 0 || q_hi > F || q_lo >= q_hi) return false;
   if (((q_hi + 15) >> 4) - (q_lo >> 4) > NWARP) return false;   // one 16-frame query tile per warp
-  return smem_bytes(F, band) <= 225 * 1024;
+  return smem_bytes(F, band, 1) <= kSmemMax;
 }
 
-int launch_temporal_fused(const TemporalFusedArgs& a, cudaStream_t st) {
-  if (!temporal_fused_supported(C, a.F, a.band, a.q_lo, a.q_hi)) { set_last_error("temporal_fused: unsupported shape"); return -1; }
+int launch_temporal_fused(const TemporalFusedArgs& a_in, cudaStream_t st) {
+  if (!temporal_fused_supported(C, a_in.F, a_in.band, a_in.q_lo, a_in.q_hi)) { set_last_error("temporal_fused: unsupported shape"); return -1; }
   static size_t attr_bytes = 0;
-  const size_t smem = smem_bytes(a.F, a.band);
+  TemporalFusedArgs a = a_in;
+  a.nbuf = smem_bytes(a.F, a.band, 2) <= kSmemMax ? 2 : 1;
+  const size_t smem = smem_bytes(a.F, a.band, a.nbuf);
   if (smem > attr_bytes) {
     DAWN_CUDA_OK(cudaFuncSetAttribute(temporal_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_bytes = smem;

@@ -20,6 +20,7 @@ struct TemporalFusedArgs {
   const float* bias;              // [8][2*band+1] relative position bias
   int band;
   float inv_wscale, inv_oscale;
+  int nbuf;                       // weight stages in shared memory (set by the launcher)
 };
 
 bool temporal_fused_supported(int C, int F, int band, int q_lo, int q_hi);
