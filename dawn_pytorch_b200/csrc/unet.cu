@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "tc_gemm.cuh"
 #include "temporal_fused.cuh"
+#include "sla_fused.cuh"
 
 namespace dawn {
 
@@ -117,6 +118,9 @@ struct AttnW {     // temporal attention / mid spatial attention (U:648-725)
 };
 struct SlaW {      // spatial linear attention (U:602-627)
   int C = 0; float Wqkv_scale = 1.f; float *Wqkv = nullptr, *wsum = nullptr, *Wqkv_img = nullptr, *WoutT = nullptr, *bout = nullptr;
+  // fused context kernel (sla_fused.cu), 64-channel levels: q-only projection + K/V weights as fp16 hi|lo images
+  float *Wq = nullptr, *wsum_q = nullptr, *Wq_img = nullptr; float Wq_scale = 1.f;
+  uint16_t* fkv = nullptr; float f_inv_wscale = 1.f;
 };
 struct UpW { ConvW cls[4]; };
 
@@ -134,6 +138,7 @@ struct dawn_unet {
   bool committed = false;
   bool use_tc = true;                          // tcgen05 contraction path (DAWN_TC=0 falls back to mma.sync)
   bool use_conv3 = true;                       // halo-tile tcgen05 3x3 conv (DAWN_TC_CONV3=0 falls back to the per-tap GEMM)
+  bool use_fused_sla = true;                   // fused SLA context on 64-channel levels (DAWN_FUSED_SLA=0: unfused)
   bool use_fused_ta = true;                    // fused per-pixel temporal attention on 64-channel levels (DAWN_FUSED_TA=0: unfused)
   bool use_attn_tc = true;                     // tensor-core attention core (DAWN_ATTN_TC=0 falls back to SIMT)
 
@@ -381,6 +386,19 @@ int pack_sla(dawn_unet* h, const std::string& p, int C, SlaW* s) {        // p =
   DAWN_TRY(need(h, p + ".fn.to_out.bias", {C}, &b));
   s->C = C;
   DAWN_TRY(pack_linear(h, qkv, 768, C, g->data.data(), 1.f, 0, &s->Wqkv, &s->wsum, nullptr, &s->Wqkv_img, &s->Wqkv_scale));
+  if (C == 64) {
+    DAWN_TRY(pack_linear(h, qkv, 256, C, g->data.data(), 1.f, 0, &s->Wq, &s->wsum_q, nullptr, &s->Wq_img, &s->Wq_scale));
+    std::vector<float> wf((size_t)768 * C);
+    for (int n = 0; n < 768; ++n)
+      for (int k = 0; k < C; ++k) wf[(size_t)n * C + k] = qkv->data[(size_t)n * C + k] * g->data[k];
+    std::vector<uint16_t> W;
+    sla_fused_pack(wf.data(), W, &s->f_inv_wscale);
+    std::vector<float> tmp(W.size() / 2);
+    memcpy(tmp.data(), W.data(), W.size() * 2);
+    float* d = nullptr;
+    DAWN_TRY(dev_upload(h, tmp, &d));
+    s->fkv = reinterpret_cast<uint16_t*>(d);
+  }
   std::vector<float> wt((size_t)256 * C);
   for (int c = 0; c < C; ++c)
     for (int k = 0; k < 256; ++k) wt[(size_t)k * C + c] = o->data[(size_t)c * 256 + k];
@@ -699,20 +717,35 @@ int mid_spatial_attn(Ctx& c, const AttnW& w, const Act& x, const std::string& na
 int sla(Ctx& c, const SlaW& w, const Act& x, const std::string& name) {
   dawn_unet* h = c.h;
   const int F = h->F, P = x.H * x.W, M = F * P;
-  {
+  const int ldb = round_up(x.C, 64);
+  const bool fused = h->use_fused_sla && w.fkv && sla_fused_supported(x.C, P) &&
+                     sla_fused_part_floats(F, P) <= (size_t)(F + 2 * h->cfg.win_width) * h->lH[0] * h->lW[0] * 256;
+  const int qld = fused ? 256 : 768;
+  if (fused) {
+    // q only through the GEMM (softmax over the head dim in its epilogue); k, v never leave the context kernel's registers
+    GemmParams p; base_params(p, x, F);
+    p.B = w.Wq; p.Bimg = w.Wq_img; p.tc_scale = 1.0f / (kTcActScale * w.Wq_scale); p.ldb = 256; p.N = 256; p.K = x.C;
+    p.wsum = w.wsum_q; p.q_post_scale = 1.0f / sqrtf(32.0f);
+    p.Out = h->QKV; p.ldo = 256;
+    DAWN_TRY(ln_gemm(c, p, EPI_QKV_SLA, PC_QKV, x.p, x.ld, x.C, M));
+    SlaCtxArgs a{};
+    a.x = x.p; a.ldx = x.ld; a.F = F; a.P = P; a.Wkv = w.fkv; a.inv_wscale = w.f_inv_wscale; a.part = h->O;
+    ProfScope ps(c, PC_SLA_CTX, 2.0 * M * x.C * 512 + 2.0 * 8 * 32 * 32 * M + 2.0 * F * 256 * 32 * x.C, 4.0 * M * x.C);
+    h->launches++;                                     // context kernel + merge kernel
+    DAWN_TRY(launch_sla_ctx_fused(a, w.WoutT, h->BF, ldb, c.st));
+  } else {
     GemmParams p; base_params(p, x, F);
     p.B = w.Wqkv; p.Bimg = w.Wqkv_img; p.tc_scale = 1.0f / (kTcActScale * w.Wqkv_scale); p.ldb = 768; p.N = 768; p.K = x.C;
     p.wsum = w.wsum; p.q_post_scale = 1.0f / sqrtf(32.0f);
     p.Out = h->QKV; p.ldo = 768;
     DAWN_TRY(ln_gemm(c, p, EPI_QKV_SLA, PC_QKV, x.p, x.ld, x.C, M));
   }
-  const int ldb = round_up(x.C, 64);
-  {
+  if (!fused) {
     ProfScope ps(c, PC_SLA_CTX, 2.0 * 8 * 32 * 32 * M + 2.0 * F * 256 * 32 * x.C, 4.0 * M * 768);
     DAWN_TRY(launch_sla_context(h->QKV, 768, F, P, w.WoutT, x.C, h->BF, ldb, c.st));
   }
   {
-    Act q{h->QKV, 768, 256, x.H, x.W};
+    Act q{h->QKV, qld, 256, x.H, x.W};
     GemmParams p; base_params(p, q, F);
     p.B = h->BF; p.ldb = ldb; p.b_batch_stride = (long long)256 * ldb; p.N = x.C; p.K = 256;
     p.rows_per_batch = P; p.bias = w.bout;
@@ -883,6 +916,7 @@ int dawn_unet_create(const dawn_unet_cfg* cfg, dawn_unet** out) {
   { const char* e = getenv("DAWN_TC"); h->use_tc = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_ATTN_TC"); h->use_attn_tc = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_FUSED_TA"); h->use_fused_ta = !(e && e[0] == '0'); }
+  { const char* e = getenv("DAWN_FUSED_SLA"); h->use_fused_sla = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_TC_CONV3"); h->use_conv3 = !(e && e[0] == '0'); }
   h->nlev = cfg->n_levels;
   h->dims.push_back(cfg->dim);
