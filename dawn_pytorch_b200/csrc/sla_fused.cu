@@ -100,33 +100,43 @@ __global__ void __launch_bounds__(NTH, 1) sla_ctx_kernel(SlaCtxArgs a) {
     lrow[mi][0] = lrow[mi][1] = 0.f;
   }
 
+  // raw pixels of the next chunk travel in registers while the current chunk is being multiplied
+  const int l16 = tid & 15;
+  float4 xin[CHUNK / (NTH / 16)];
+  auto fetch = [&](int p0) {
+#pragma unroll
+    for (int i = 0; i < CHUNK / (NTH / 16); ++i) {
+      const int px = p0 + i * (NTH / 16) + (tid >> 4);
+      xin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (px < px_hi) xin[i] = __ldg(reinterpret_cast<const float4*>(a.x + ((size_t)f * a.P + px) * a.ldx) + l16);
+    }
+  };
+  fetch(px_lo);
+
   for (int p0 = px_lo; p0 < px_hi; p0 += CHUNK) {
     __syncthreads();                                    // previous chunk consumed
     // ---------------------------------------------------------------- stage CHUNK pixels: LayerNorm over channels, fp16 hi/lo
-    {
-      const int l16 = tid & 15;
 #pragma unroll
-      for (int r0 = 0; r0 < CHUNK; r0 += NTH / 16) {
-        const int r = r0 + (tid >> 4), px = p0 + r;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (px < px_hi) v = __ldg(reinterpret_cast<const float4*>(a.x + ((size_t)f * a.P + px) * a.ldx) + l16);
-        float s = (v.x + v.y) + (v.z + v.w);
+    for (int i = 0; i < CHUNK / (NTH / 16); ++i) {
+      const int r = i * (NTH / 16) + (tid >> 4);
+      const float4 v = xin[i];
+      float s = (v.x + v.y) + (v.z + v.w);
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float mu = s * (1.0f / C);
-        const float d0 = v.x - mu, d1 = v.y - mu, d2 = v.z - mu, d3 = v.w - mu;
-        float ss = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+      for (int o = 1; o < 16; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mu = s * (1.0f / C);
+      const float d0 = v.x - mu, d1 = v.y - mu, d2 = v.z - mu, d3 = v.w - mu;
+      float ss = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        const float rs = 1.0f / sqrtf(ss * (1.0f / C) + 1e-5f);
-        uint32_t h0, l0, h1, l1;
-        split2h(d0 * rs, d1 * rs, h0, l0); split2h(d2 * rs, d3 * rs, h1, l1);
-        *reinterpret_cast<uint2*>(&Xh[r * LD + l16 * 4]) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(&Xl[r * LD + l16 * 4]) = make_uint2(l0, l1);
-      }
+      for (int o = 1; o < 16; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rs = 1.0f / sqrtf(ss * (1.0f / C) + 1e-5f);
+      uint32_t h0, l0, h1, l1;
+      split2h(d0 * rs, d1 * rs, h0, l0); split2h(d2 * rs, d3 * rs, h1, l1);
+      *reinterpret_cast<uint2*>(&Xh[r * LD + l16 * 4]) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(&Xl[r * LD + l16 * 4]) = make_uint2(l0, l1);
     }
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
+    if (p0 + CHUNK < px_hi) fetch(p0 + CHUNK);
 
     const int ngrp = min(CHUNK, px_hi - p0) >> 4;       // 16-pixel groups (P is a multiple of 16)
     for (int grp = 0; grp < ngrp; ++grp) {

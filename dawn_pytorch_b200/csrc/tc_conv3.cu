@@ -39,7 +39,10 @@ struct CCfg {
   static constexpr int NTHREADS = NPROD + 128 * NWG + 64;
   static constexpr int MMA_WARP = (NPROD + 128 * NWG) / 32;
   static constexpr int LOAD_WARP = MMA_WARP + 1;
-  static constexpr int TMEM_COLS = 2 * BN;
+  // BN == 64: one N=128 MMA multiplies A_hi with [B_hi | B_lo] (two 64-column accumulators, summed by the epilogue):
+  // 2 instead of 3 instructions per k-step, and the N=64 instruction was issue-bound at about the cost of an N=128 one.
+  static constexpr int ACC_COLS = (BN == 64) ? 128 : BN;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
 };
 
 template <int BN>
@@ -47,7 +50,7 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
                                                                           int tiles_y, int tiles_x, int tiles_n) {
   using C = CCfg<BN>;
   constexpr int B_PANEL = C::B_PANEL, A_STAGES = C::A_STAGES, B_STAGES = C::B_STAGES, NWG = C::NWG;
-  constexpr int MMA_WARP = C::MMA_WARP, LOAD_WARP = C::LOAD_WARP, TMEM_COLS = C::TMEM_COLS;
+  constexpr int MMA_WARP = C::MMA_WARP, LOAD_WARP = C::LOAD_WARP, TMEM_COLS = C::TMEM_COLS, ACC_COLS = C::ACC_COLS;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t a_full[A_STAGES], a_free[A_STAGES], b_full[B_STAGES], b_free[B_STAGES], acc_full[2], acc_free[2];
   __shared__ uint32_t s_tmem_base;
@@ -159,6 +162,7 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
     // =============================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       constexpr uint64_t SBO_HALO = (uint64_t)(HW * 128 / 16);   // 10 pixel rows of 128 B between 8-row groups
       uint32_t ait = 0, bit = 0, cg = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
           fence_proxy_async();
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smemA + sa * 2 * A_HALO), a_lo = a_hi + A_HALO;
-          const uint32_t d = tmem_base + buf * BN;
+          const uint32_t d = tmem_base + buf * ACC_COLS;
           for (int tap = 0; tap < 9; ++tap, ++bit) {
             const int sb = bit % B_STAGES;
             mbar_wait(&b_full[sb], (bit / B_STAGES) & 1);
@@ -185,9 +189,15 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint64_t o = (uint64_t)(j * 2);
-              tc_mma_f16(d, alo + o, bhi + o, idesc, (tap == 0 && j == 0) ? 0u : 1u);
-              tc_mma_f16(d, ahi + o, blo + o, idesc, 1u);
-              tc_mma_f16(d, ahi + o, bhi + o, idesc, 1u);
+              if (BN == 64) {
+                // the lo panel follows the hi panel in the stage: rows 64..127 of one N=128 operand
+                tc_mma_f16(d, ahi + o, bhi + o, idesc2, (tap == 0 && j == 0) ? 0u : 1u);
+                tc_mma_f16(d, alo + o, bhi + o, idesc, 1u);
+              } else {
+                tc_mma_f16(d, alo + o, bhi + o, idesc, (tap == 0 && j == 0) ? 0u : 1u);
+                tc_mma_f16(d, ahi + o, blo + o, idesc, 1u);
+                tc_mma_f16(d, ahi + o, bhi + o, idesc, 1u);
+              }
             }
             tc_commit(&b_free[sb]);
           }
@@ -220,9 +230,14 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float v[16];
-          tmem_ld16(tmem_base + lane_addr + buf * BN + wg * 64 + q * 16, v);
+          tmem_ld16(tmem_base + lane_addr + buf * ACC_COLS + wg * 64 + q * 16, v);
 #pragma unroll
           for (int i = 0; i < 16; ++i) acc[q * 16 + i] += v[i];
+          if (BN == 64) {                                         // hi*lo partial products live in the second 64 columns
+            tmem_ld16(tmem_base + lane_addr + buf * ACC_COLS + 64 + q * 16, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[q * 16 + i] += v[i];
+          }
         }
         tc_fence_before();
         mbar_arrive(&acc_free[buf]);
