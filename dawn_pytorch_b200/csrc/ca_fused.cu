@@ -1,0 +1,298 @@
+// Cross-attention gate weights of a conditioned ResnetBlock (reference U:454-463, 505-560), fused for ci <= 128:
+//
+//   x (block input, M x ci)  ->  LayerNorm_img  ->  q = x^ Wq (3 cross-attentions x 8 heads x 8 dims)
+//      ->  per head: cosine-similarity logits against the frame's key and the null key, 2-way softmax  ->  gate
+//      ->  per cross-attention: rstd of the LayerNorm'd to_out output from the 9x9 Gram form  ->  Wt (M x 32)
+//
+// Every frame has exactly two keys per cross-attention (its conditioning token and the learned null token), so the attention output
+// is an affine function of one gate per head; unet.cu folds to_out / LayerNorm into per-frame tables (T, G) and the block only needs
+// Wt = rstd * [1, gate_0..7] per cross-attention.  The unfused path ran a tcgen05 GEMM with N = 192 (three 64-column tiles, each
+// re-gathering and re-splitting the A rows; gates through HBM) plus ca_rstd_kernel.  Here a warp owns 16 pixels: q comes out of
+// mma.sync (3-term FP16 split, fp32 accumulate) 64 columns at a time, the accumulator layout gives each quad one head per n-tile, and
+// the gates never leave the SM.
+#include <cuda_fp16.h>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "common.cuh"
+#include "kernels.cuh"
+#include "ca_fused.cuh"
+
+namespace dawn {
+namespace {
+
+constexpr int NTH = 256;
+constexpr int CHUNK = 128;             // pixels staged per iteration: one 16-pixel group per warp
+constexpr int WT_LD = 36;              // floats per row of a warp's gate / Wt patch (bank-conflict-free column writes)
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], const __half* p) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void split2h(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const float h0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
+  const float h1 = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+  const __half2 h = __floats2half2_rn(h0, h1);
+  const __half2 l = __floats2half2_rn(x0 - h0, x1 - h1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+template <int CI>
+__global__ void __launch_bounds__(NTH, (CI == 64) ? 2 : 1) ca_wt_kernel(CaFusedArgs a) {
+  constexpr int LD = CI + 8;                            // halfs per shared-memory row
+  constexpr int LPR = CI / 4;                           // lanes (float4 each) per pixel row
+  constexpr int RPP = NTH / LPR;                        // rows per staging pass
+  constexpr int NPASS = CHUNK / RPP;
+  constexpr int KS = CI / 16;
+  extern __shared__ __align__(16) unsigned char ca_smem[];
+  __half* Wh = reinterpret_cast<__half*>(ca_smem);      // [192][LD] hi
+  __half* Wl = Wh + 192 * LD;
+  __half* Xh = Wl + 192 * LD;                           // [CHUNK][LD]
+  __half* Xl = Xh + CHUNK * LD;
+  float* s_kq = reinterpret_cast<float*>(Xl + CHUNK * LD);   // [3][64] this frame's projected keys (q/k scales folded)
+  float* s_nk = s_kq + 192;                             // [3][8] null keys
+  float* s_G = s_nk + 24;                               // [3][81] Gram forms
+  float* s_wt = s_G + 244;                              // [8 warps][16][WT_LD] gate / Wt patch
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3, lm = lane >> 3, lr = lane & 7;
+  const int f = blockIdx.y, split = blockIdx.x;
+  const int px_lo = split * a.px_per_cta, px_hi = min(a.P, px_lo + a.px_per_cta);
+
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.Wq);      // dense [hi|lo][192][CI] fp16
+    for (int i = tid; i < 2 * 192 * CI / 8; i += NTH) {
+      const int r = i / (CI / 8), c8 = i - r * (CI / 8);
+      cp_async_16(Wh + r * LD + c8 * 8, src + i);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    for (int i = tid; i < 192; i += NTH) s_kq[i] = a.kq[(size_t)f * 192 + i];
+    if (tid < 24) s_nk[tid] = a.nkq[tid];
+    for (int i = tid; i < 243; i += NTH) s_G[i] = a.G[(size_t)f * 243 + i];
+  }
+
+  const int lrow = tid % LPR;
+  float4 xin[NPASS];
+  auto fetch = [&](int p0) {
+#pragma unroll
+    for (int i = 0; i < NPASS; ++i) {
+      const int px = p0 + i * RPP + tid / LPR;
+      xin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (px < px_hi) xin[i] = __ldg(reinterpret_cast<const float4*>(a.x + ((size_t)f * a.P + px) * a.ldx) + lrow);
+    }
+  };
+  fetch(px_lo);
+  float* wt = s_wt + warp * 16 * WT_LD;
+
+  for (int p0 = px_lo; p0 < px_hi; p0 += CHUNK) {
+    __syncthreads();
+    // ---------------------------------------------------------------- stage CHUNK pixels: LayerNorm_img, fp16 hi/lo
+#pragma unroll
+    for (int i = 0; i < NPASS; ++i) {
+      const int r = i * RPP + tid / LPR;
+      const float4 v = xin[i];
+      float s = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+      for (int o = 1; o < LPR; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mu = s * (1.0f / CI);
+      const float d0 = v.x - mu, d1 = v.y - mu, d2 = v.z - mu, d3 = v.w - mu;
+      float ss = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+#pragma unroll
+      for (int o = 1; o < LPR; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rs = 1.0f / sqrtf(ss * (1.0f / CI) + 1e-5f);
+      uint32_t h0, l0, h1, l1;
+      split2h(d0 * rs, d1 * rs, h0, l0); split2h(d2 * rs, d3 * rs, h1, l1);
+      *reinterpret_cast<uint2*>(&Xh[r * LD + lrow * 4]) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(&Xl[r * LD + lrow * 4]) = make_uint2(l0, l1);
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
+    if (p0 + CHUNK < px_hi) fetch(p0 + CHUNK);
+
+    const int grp0 = p0 + warp * 16;                    // this warp's 16 pixels
+    if (grp0 >= px_hi) continue;
+    // A fragments of the 16 x CI pixel tile
+    uint32_t ah[KS][4], al[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int aoff = (warp * 16 + (lm & 1) * 8 + lr) * LD + ks * 16 + (lm >> 1) * 8;
+      ldsm4(ah[ks], Xh + aoff);
+      ldsm4(al[ks], Xl + aoff);
+    }
+#pragma unroll 1
+    for (int ca = 0; ca < 3; ++ca) {
+      float q[8][4];                                    // n-tile = head, columns 2t, 2t+1 = head dims
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) q[n][c] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          uint32_t b[4];
+          ldsm4(b, ((lm & 2) ? Wl : Wh) + (ca * 64 + n * 8 + lr) * LD + ks * 16 + (lm & 1) * 8);
+          mma16816(q[n], al[ks], b[0], b[1]);
+          mma16816(q[n], ah[ks], b[2], b[3]);
+          mma16816(q[n], ah[ks], b[0], b[1]);
+        }
+      // per-lane partial sums over its two head dims: |q|^2, q.k, q.k_null for rows g (a) and g+8 (b) of every head
+      const float2 nk = *reinterpret_cast<const float2*>(s_nk + ca * 8 + 2 * t);
+      float v[8][6];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const float2 k = *reinterpret_cast<const float2*>(s_kq + ca * 64 + n * 8 + 2 * t);
+        const float q0 = q[n][0] * a.inv_wscale, q1 = q[n][1] * a.inv_wscale, q2 = q[n][2] * a.inv_wscale, q3 = q[n][3] * a.inv_wscale;
+        v[n][0] = q0 * q0 + q1 * q1; v[n][1] = q0 * k.x + q1 * k.y; v[n][2] = q0 * nk.x + q1 * nk.y;
+        v[n][3] = q2 * q2 + q3 * q3; v[n][4] = q2 * k.x + q3 * k.y; v[n][5] = q2 * nk.x + q3 * nk.y;
+      }
+      // reduce-scatter over the quad: lane t ends up with the complete sums of heads t and t + 4
+      float w[4][6], u[2][6];
+      const bool odd = t & 1, hi2 = t & 2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) {
+          const float send = odd ? v[2 * j][e] : v[2 * j + 1][e];
+          const float keep = odd ? v[2 * j + 1][e] : v[2 * j][e];
+          w[j][e] = keep + __shfl_xor_sync(0xffffffffu, send, 1);          // head 2j + (t & 1)
+        }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) {
+          const float send = hi2 ? w[2 * j][e] : w[2 * j + 1][e];
+          const float keep = hi2 ? w[2 * j + 1][e] : w[2 * j][e];
+          u[j][e] = keep + __shfl_xor_sync(0xffffffffu, send, 2);          // head 4j + t
+        }
+      // l2-normalised q (F.normalize, eps 1e-12) x scale 8; two-way softmax over {key, null key} = sigmoid(s_key - s_null)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const float n2 = u[j][3 * r], dr = u[j][3 * r + 1], dn = u[j][3 * r + 2];
+          const float inv = 8.0f * rsqrtf(fmaxf(n2, 1e-24f));
+          const float gate = __fdividef(1.0f, 1.0f + __expf((dn - dr) * inv));
+          wt[(g + 8 * r) * WT_LD + ca * 8 + 4 * j + t] = gate;
+        }
+    }
+    __syncwarp();
+    // ---------------------------------------------------------------- rstd from the Gram form; Wt row = [rs*[1, gates] x 3, 0 x 5]
+    float outv[2][9];
+    float rsv[2];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int item = lane + 32 * it;                  // (row, ca): 48 items
+      const int row = item / 3, ca = item - row * 3;
+      if (item < 48) {
+        float c[9];
+        c[0] = 1.f;
+#pragma unroll
+        for (int hd = 0; hd < 8; ++hd) c[hd + 1] = wt[row * WT_LD + ca * 8 + hd];
+        const float* G = s_G + ca * 81;
+        float var = 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          float rowv = 0.f;
+#pragma unroll
+          for (int j = 0; j < 9; ++j) rowv += G[i * 9 + j] * c[j];
+          var += c[i] * rowv;
+        }
+        rsv[it] = rsqrtf(fmaxf(var, 0.f) + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) outv[it][i] = rsv[it] * c[i];
+      }
+    }
+    __syncwarp();                                       // all gates read before the patch is overwritten
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int item = lane + 32 * it;
+      const int row = item / 3, ca = item - row * 3;
+      if (item < 48) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) wt[row * WT_LD + ca * 9 + i] = outv[it][i];
+      }
+    }
+    if (lane < 16) {
+#pragma unroll
+      for (int k = 27; k < 32; ++k) wt[lane * WT_LD + k] = 0.f;
+    }
+    __syncwarp();
+    // 16 rows x 128 B are contiguous in Wt (ld 32): coalesced float4 stores
+    float4* dst = reinterpret_cast<float4*>(a.Wt + ((size_t)f * a.P + grp0) * 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = lane + 32 * i;                    // float4 index in the dense 16 x 32 tile
+      dst[idx] = *reinterpret_cast<const float4*>(wt + (idx >> 3) * WT_LD + (idx & 7) * 4);
+    }
+    __syncwarp();
+  }
+}
+
+template <int CI>
+constexpr size_t smem_bytes() { return (size_t)(2 * 192 * (CI + 8) + 2 * CHUNK * (CI + 8)) * 2 + (size_t)(192 + 24 + 244 + 8 * 16 * WT_LD) * 4; }
+
+template <int CI>
+int launch_ci(CaFusedArgs a, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    DAWN_CUDA_OK(cudaFuncSetAttribute(ca_wt_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<CI>()));
+    attr = true;
+  }
+  // pixel runs of 512 (fewer for small frames): F * splits CTAs
+  int px = 512;
+  while (px > CHUNK && a.P % px != 0) px >>= 1;
+  a.px_per_cta = px;
+  const int nsplit = (a.P + px - 1) / px;
+  ca_wt_kernel<CI><<<dim3(nsplit, a.F), NTH, smem_bytes<CI>(), st>>>(a);
+  DAWN_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace
+
+bool ca_fused_supported(int ci, int P) { return (ci == 64 || ci == 128) && P % 16 == 0 && P >= CHUNK; }
+
+int launch_ca_fused(const CaFusedArgs& a, int ci, cudaStream_t st) {
+  if (!ca_fused_supported(ci, a.P)) { set_last_error("ca_fused: unsupported shape"); return -1; }
+  return ci == 64 ? launch_ci<64>(a, st) : launch_ci<128>(a, st);
+}
+
+// wq: [ci][192] folded projection (k-major, as the GEMM path packs it) -> [hi|lo][192][ci] fp16 with a power-of-two pre-scale
+void ca_fused_pack(const float* wq, int ci, std::vector<uint16_t>& W, float* inv_wscale) {
+  float mx = 0.f;
+  for (size_t i = 0; i < (size_t)ci * 192; ++i) mx = std::max(mx, std::fabs(wq[i]));
+  int e = 0;
+  if (mx > 0.f) std::frexp(mx, &e);
+  const float sc = std::ldexp(1.0f, 11 - e);
+  *inv_wscale = 1.0f / sc;
+  W.assign((size_t)2 * 192 * ci, 0);
+  for (int n = 0; n < 192; ++n)
+    for (int k = 0; k < ci; ++k) {
+      const float v = wq[(size_t)k * 192 + n] * sc;
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      memcpy(&W[(size_t)n * ci + k], &hi, 2);
+      memcpy(&W[((size_t)192 + n) * ci + k], &lo, 2);
+    }
+}
+
+}  // namespace dawn

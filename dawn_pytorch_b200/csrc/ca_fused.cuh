@@ -1,0 +1,25 @@
+// Fused cross-attention gate weights (LayerNorm_img + q projection + 2-key softmax gates + Gram-form rstd); see ca_fused.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <vector>
+
+namespace dawn {
+
+struct CaFusedArgs {
+  const float* x; int ldx;        // block input, rows f*P + pixel, ci channels
+  int F, P;
+  const uint16_t* Wq;             // [hi|lo][192][ci] fp16, LayerNorm gain folded, pre-scaled by 1/inv_wscale
+  float inv_wscale;
+  const float* kq;                // [F][3][64] projected keys of the frame's conditioning tokens
+  const float* nkq;               // [3][8] null keys
+  const float* G;                 // [F][3][81] Gram forms of the folded to_out / LayerNorm
+  float* Wt;                      // [F*P][32] output: rstd * [1, gate_0..7] per cross-attention, 5 zero columns
+  int px_per_cta;                 // set by the launcher
+};
+
+bool ca_fused_supported(int ci, int P);
+int launch_ca_fused(const CaFusedArgs& a, int ci, cudaStream_t st);
+void ca_fused_pack(const float* wq_kmajor, int ci, std::vector<uint16_t>& W, float* inv_wscale);
+
+}  // namespace dawn

@@ -17,6 +17,7 @@
 #include "tc_gemm.cuh"
 #include "temporal_fused.cuh"
 #include "sla_fused.cuh"
+#include "ca_fused.cuh"
 
 namespace dawn {
 
@@ -104,6 +105,7 @@ struct ResBlockW {
   float *mW[3] = {nullptr, nullptr, nullptr}, *mB[3] = {nullptr, nullptr, nullptr};   // pose, aud, eye MLPs
   float Wq_scale = 1.f;
   float *Wq = nullptr, *wsumq = nullptr, *Wq_img = nullptr;                              // [ci][192], [192]
+  uint16_t* fWq = nullptr; float f_inv_wscale = 1.f;                                      // ca_fused.cu image (ci <= 128)
   CrossAttnW ca[3];
   // per-clip (depend on F / cond)
   float *film = nullptr, *kq = nullptr, *nkq = nullptr, *T = nullptr, *G = nullptr;
@@ -138,6 +140,7 @@ struct dawn_unet {
   bool committed = false;
   bool use_tc = true;                          // tcgen05 contraction path (DAWN_TC=0 falls back to mma.sync)
   bool use_conv3 = true;                       // halo-tile tcgen05 3x3 conv (DAWN_TC_CONV3=0 falls back to the per-tap GEMM)
+  bool use_fused_ca = true;                    // fused cross-attention gate kernel for ci <= 128 (DAWN_FUSED_CA=0: unfused)
   bool use_fused_sla = true;                   // fused SLA context on 64-channel levels (DAWN_FUSED_SLA=0: unfused)
   bool use_fused_ta = true;                    // fused per-pixel temporal attention on 64-channel levels (DAWN_FUSED_TA=0: unfused)
   bool use_attn_tc = true;                     // tensor-core attention core (DAWN_ATTN_TC=0 falls back to SIMT)
@@ -346,6 +349,15 @@ int pack_resblock(dawn_unet* h, const std::string& name, int ci, int co, bool co
     DAWN_TRY(dev_upload(h, wq, &r.Wq));
     DAWN_TRY(upload_tc_image(h, wq, ci, 192, 192, &r.Wq_img, &r.Wq_scale));
     DAWN_TRY(dev_upload(h, wsum, &r.wsumq));
+    if (ci == 64 || ci == 128) {
+      std::vector<uint16_t> W;
+      ca_fused_pack(wq.data(), ci, W, &r.f_inv_wscale);
+      std::vector<float> tmp(W.size() / 2);
+      memcpy(tmp.data(), W.data(), W.size() * 2);
+      float* d = nullptr;
+      DAWN_TRY(dev_upload(h, tmp, &d));
+      r.fWq = reinterpret_cast<uint16_t*>(d);
+    }
   }
   h->rb_index[name] = (int)h->rb.size();
   h->rb.push_back(r);
@@ -559,7 +571,13 @@ int resblock(Ctx& c, const ResBlockW& r, const Act& x, const Act& out) {
   DAWN_CHECK(x.C == r.ci && out.C == r.co, "resblock channel mismatch: " + r.name);
   Act y{h->Y, r.co, r.co, x.H, x.W}, a1{h->A1, r.co, r.co, x.H, x.W};
   const double count = (double)h->sh_Fglobal * P * (r.co / 8);     // GroupNorm statistics span the WHOLE clip (U:230)
-  if (r.cond) {
+  if (r.cond && h->use_fused_ca && r.fWq && ca_fused_supported(r.ci, P)) {
+    CaFusedArgs a{};
+    a.x = x.p; a.ldx = x.ld; a.F = F; a.P = P; a.Wq = r.fWq; a.inv_wscale = r.f_inv_wscale;
+    a.kq = r.kq; a.nkq = r.nkq; a.G = r.G; a.Wt = h->WT;
+    ProfScope ps(c, PC_CA_GATE, 2.0 * M * r.ci * 192, 4.0 * M * (r.ci + 32));
+    DAWN_TRY(launch_ca_fused(a, r.ci, c.st));
+  } else if (r.cond) {
     // cross-attention gates from the raw block input (U:454-463): LayerNorm_img folded into the q projection
     GemmParams p; base_params(p, x, F);
     p.B = r.Wq; p.Bimg = r.Wq_img; p.tc_scale = 1.0f / (kTcActScale * r.Wq_scale); p.ldb = 192; p.N = 192; p.K = r.ci;
@@ -917,6 +935,7 @@ int dawn_unet_create(const dawn_unet_cfg* cfg, dawn_unet** out) {
   { const char* e = getenv("DAWN_ATTN_TC"); h->use_attn_tc = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_FUSED_TA"); h->use_fused_ta = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_FUSED_SLA"); h->use_fused_sla = !(e && e[0] == '0'); }
+  { const char* e = getenv("DAWN_FUSED_CA"); h->use_fused_ca = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_TC_CONV3"); h->use_conv3 = !(e && e[0] == '0'); }
   h->nlev = cfg->n_levels;
   h->dims.push_back(cfg->dim);
