@@ -267,7 +267,111 @@ int launch_ci(CaFusedArgs a, cudaStream_t st) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// a1 = SiLU(FiLM(GroupNorm(y))) + Wt (M x 32) * T_f (32 x co)      (first half of a conditioned ResnetBlock, U:366-380, 454-463)
+// A streaming kernel: Wt rows arrive straight in A-fragment order from global memory, the frame's table T_f sits in shared memory as
+// fp16 hi|lo, the K = 32 product is 6 mma.sync per 8 channels, and the epilogue reads y / writes a1 in 32-byte quad segments.
+__global__ void __launch_bounds__(NTH) gn_hcond_kernel(GnHcondArgs a) {
+  constexpr int TLD = 40;
+  extern __shared__ __align__(16) unsigned char gh_smem[];
+  __half* Th = reinterpret_cast<__half*>(gh_smem);      // [co][TLD]  B operand: rows = output channel, k = table row
+  __half* Tl = Th + a.co * TLD;
+  float* s_al = reinterpret_cast<float*>(Tl + a.co * TLD);     // per channel: t = y * al + be
+  float* s_be = s_al + a.co;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3, lm = lane >> 3, lr = lane & 7;
+  const int f = blockIdx.y;
+  const int px_lo = blockIdx.x * a.px_per_cta, px_hi = min(a.P, px_lo + a.px_per_cta);
+  const int co = a.co;
+
+  {
+    const float* T = a.T + (size_t)f * 32 * a.ldbT;
+    for (int i = tid; i < 32 * co; i += NTH) {
+      const int k = i / co, c = i - k * co;
+      const float v = T[(size_t)k * a.ldbT + c];
+      const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+      Th[c * TLD + k] = __float2half_rn(h);
+      Tl[c * TLD + k] = __float2half_rn(v - h);
+    }
+    for (int c = tid; c < co; c += NTH) {
+      const int grp = c / a.cpg;
+      const double sm = a.gn_stats[2 * grp], ss = a.gn_stats[2 * grp + 1];
+      const double mean = sm / a.gn_count;
+      const double var = ss / a.gn_count - mean * mean;
+      const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+      float al = rstd * a.gn_w[c], be = a.gn_b[c] - (float)mean * al;
+      if (a.film) { const float sc = a.film[c] + 1.f; al *= sc; be = be * sc + a.film[co + c]; }
+      s_al[c] = al; s_be[c] = be;
+    }
+  }
+  __syncthreads();
+
+  for (int p0 = px_lo + warp * 16; p0 < px_hi; p0 += 16 * (NTH / 32)) {
+    const size_t row0 = (size_t)f * a.P + p0 + g, row1 = row0 + 8;
+    // Wt rows in A-fragment order: (row g | g+8) x (k = ks*16 + {0, 8} + 2t, 2t+1)
+    uint32_t ah[2][4], al[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const float2 v0 = __ldg(reinterpret_cast<const float2*>(a.Wt + row0 * 32 + ks * 16 + 2 * t));
+      const float2 v1 = __ldg(reinterpret_cast<const float2*>(a.Wt + row1 * 32 + ks * 16 + 2 * t));
+      const float2 v2 = __ldg(reinterpret_cast<const float2*>(a.Wt + row0 * 32 + ks * 16 + 8 + 2 * t));
+      const float2 v3 = __ldg(reinterpret_cast<const float2*>(a.Wt + row1 * 32 + ks * 16 + 8 + 2 * t));
+      split2h(v0.x, v0.y, ah[ks][0], al[ks][0]); split2h(v1.x, v1.y, ah[ks][1], al[ks][1]);
+      split2h(v2.x, v2.y, ah[ks][2], al[ks][2]); split2h(v3.x, v3.y, ah[ks][3], al[ks][3]);
+    }
+    const float* y0 = a.Y + row0 * a.ldy;
+    const float* y1 = a.Y + row1 * a.ldy;
+    float* o0 = a.Out + row0 * a.ldo;
+    float* o1 = a.Out + row1 * a.ldo;
+    for (int n0 = 0; n0 < co; n0 += 32) {
+      float2 yv[4][2];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {                     // issue the y loads ahead of the tensor-core work
+        yv[n][0] = __ldg(reinterpret_cast<const float2*>(y0 + n0 + n * 8 + 2 * t));
+        yv[n][1] = __ldg(reinterpret_cast<const float2*>(y1 + n0 + n * 8 + 2 * t));
+      }
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t b[4];
+          ldsm4(b, ((lm & 2) ? Tl : Th) + (n0 + n * 8 + lr) * TLD + ks * 16 + (lm & 1) * 8);
+          mma16816(acc, al[ks], b[0], b[1]);
+          mma16816(acc, ah[ks], b[2], b[3]);
+          mma16816(acc, ah[ks], b[0], b[1]);
+        }
+        const int c = n0 + n * 8 + 2 * t;
+        const float2 al2 = *reinterpret_cast<const float2*>(s_al + c), be2 = *reinterpret_cast<const float2*>(s_be + c);
+        const float t00 = yv[n][0].x * al2.x + be2.x, t01 = yv[n][0].y * al2.y + be2.y;
+        const float t10 = yv[n][1].x * al2.x + be2.x, t11 = yv[n][1].y * al2.y + be2.y;
+        *reinterpret_cast<float2*>(o0 + c) = make_float2(silu(t00) + acc[0], silu(t01) + acc[1]);
+        *reinterpret_cast<float2*>(o1 + c) = make_float2(silu(t10) + acc[2], silu(t11) + acc[3]);
+      }
+    }
+  }
+}
+
 }  // namespace
+
+bool gn_hcond_supported(int co, int P) { return co % 32 == 0 && co <= 512 && P % 16 == 0; }
+
+int launch_gn_hcond(const GnHcondArgs& a_in, cudaStream_t st) {
+  GnHcondArgs a = a_in;
+  if (!gn_hcond_supported(a.co, a.P)) { set_last_error("gn_hcond: unsupported shape"); return -1; }
+  const size_t smem = (size_t)2 * a.co * 40 * 2 + (size_t)2 * a.co * 4;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    DAWN_CUDA_OK(cudaFuncSetAttribute(gn_hcond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  int px = 512;
+  while (px > 128 && a.F * ((a.P + px - 1) / px) < 2 * 148) px >>= 1;     // enough CTAs to fill the SMs on the small levels
+  a.px_per_cta = px;
+  gn_hcond_kernel<<<dim3((a.P + px - 1) / px, a.F), NTH, smem, st>>>(a);
+  DAWN_LAUNCH_OK();
+  return 0;
+}
 
 bool ca_fused_supported(int ci, int P) { return (ci == 64 || ci == 128) && P % 16 == 0 && P >= CHUNK; }
 

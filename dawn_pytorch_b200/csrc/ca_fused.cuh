@@ -18,6 +18,19 @@ struct CaFusedArgs {
   int px_per_cta;                 // set by the launcher
 };
 
+struct GnHcondArgs {
+  const float* Wt;                // [F*P][32] gate weights (ca_fused / ca_rstd)
+  const float* T; int ldbT;       // [F][32][ldbT] per-frame tables
+  const float* Y; int ldy;        // conv1 output
+  float* Out; int ldo;            // a1
+  int F, P, co;
+  const double* gn_stats; double gn_count; int cpg;     // clip-wide GroupNorm sums (sum, sumsq per group)
+  const float *gn_w, *gn_b, *film;                     // film: [2*co] (scale | shift) or nullptr
+  int px_per_cta;                 // set by the launcher
+};
+bool gn_hcond_supported(int co, int P);
+int launch_gn_hcond(const GnHcondArgs& a, cudaStream_t st);
+
 bool ca_fused_supported(int ci, int P);
 int launch_ca_fused(const CaFusedArgs& a, int ci, cudaStream_t st);
 void ca_fused_pack(const float* wq_kmajor, int ci, std::vector<uint16_t>& W, float* inv_wscale);

@@ -606,8 +606,92 @@ __global__ void init_conv_x3_kernel(const float* __restrict__ xt, int F, int H, 
     *reinterpret_cast<float4*>(out + (size_t)pix * ldo + c4) = acc;
   }
 }
+// register-tiled variant for the 64-channel model family: a block owns 8 output rows x 64 columns of one frame, a thread 4 pixels x 8
+// channels (32 accumulators).  One (channel, ky) input row segment of 4 + KS - 1 values feeds KS x 32 FMAs, so shared-memory traffic
+// per FMA drops ~4x against the one-pixel-per-thread kernel above, which was bound by its weight reads.
+template <int KS>
+__global__ void __launch_bounds__(128) init_conv_x3_tiled_kernel(const float* __restrict__ xt, int F, int H, int W,
+                                                                 const float* __restrict__ w3, const float* __restrict__ map,
+                                                                 float* __restrict__ out, int ldo) {
+  constexpr int PAD = KS / 2, TW = 64, TR = 8, IR = TR + KS - 1, ILD = 72, NW = KS * KS * 3 * 64;
+  extern __shared__ __align__(16) float sm_ic[];
+  float* sw = sm_ic;                            // [KS*KS*3][64]
+  float* sx = sm_ic + NW;                       // [3][IR][ILD]
+  const int tid = threadIdx.x;
+  const int f = blockIdx.z, y0 = blockIdx.y * TR, x0 = blockIdx.x * TW;
+  for (int i = tid; i < NW / 4; i += 128) reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(w3) + i);
+  for (int i = tid; i < 3 * IR * ILD; i += 128) {
+    const int c = i / (IR * ILD), rem = i - c * IR * ILD, r = rem / ILD, col = rem - r * ILD;
+    const int iy = y0 + r - PAD, ix = x0 + col - PAD;
+    float v = 0.f;
+    if (col < TW + KS - 1 && iy >= 0 && iy < H && ix >= 0 && ix < W) v = xt[(((size_t)c * F + f) * H + iy) * W + ix];
+    sx[i] = v;
+  }
+  __syncthreads();
+  const int pxg = tid >> 3, cg = tid & 7;
+  for (int r = 0; r < TR; ++r) {
+    const int y = y0 + r;
+    if (y >= H) break;
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int x = x0 + pxg * 4 + i;
+      if (x < W) {
+        const float4 m0 = __ldg(reinterpret_cast<const float4*>(map + ((size_t)y * W + x) * 64 + cg * 8));
+        const float4 m1 = __ldg(reinterpret_cast<const float4*>(map + ((size_t)y * W + x) * 64 + cg * 8 + 4));
+        acc[i][0] = m0.x; acc[i][1] = m0.y; acc[i][2] = m0.z; acc[i][3] = m0.w;
+        acc[i][4] = m1.x; acc[i][5] = m1.y; acc[i][6] = m1.z; acc[i][7] = m1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+      }
+    }
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c)
+#pragma unroll 1
+      for (int ky = 0; ky < KS; ++ky) {
+        const float* row = sx + (c * IR + r + ky) * ILD + pxg * 4;
+        float xv[12];
+        *reinterpret_cast<float4*>(xv) = *reinterpret_cast<const float4*>(row);
+        *reinterpret_cast<float4*>(xv + 4) = *reinterpret_cast<const float4*>(row + 4);
+        *reinterpret_cast<float4*>(xv + 8) = *reinterpret_cast<const float4*>(row + 8);
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+          const float* wp = sw + ((ky * KS + kx) * 3 + c) * 64 + cg * 8;
+          const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float xx = xv[i + kx];
+            acc[i][0] += xx * w0.x; acc[i][1] += xx * w0.y; acc[i][2] += xx * w0.z; acc[i][3] += xx * w0.w;
+            acc[i][4] += xx * w1.x; acc[i][5] += xx * w1.y; acc[i][6] += xx * w1.z; acc[i][7] += xx * w1.w;
+          }
+        }
+      }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int x = x0 + pxg * 4 + i;
+      if (x < W) {
+        float* dst = out + ((size_t)f * H * W + (size_t)y * W + x) * ldo + cg * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+      }
+    }
+  }
+}
+
 int launch_init_conv_x3(const float* xt, int F, int H, int W, const float* w3, const float* map, int Co,
                         float* out, int ldo, int ksz, cudaStream_t st) {
+  if (ksz == 7 && Co == 64) {
+    constexpr size_t smem_t = (size_t)(7 * 7 * 3 * 64 + 3 * (8 + 6) * 72) * sizeof(float);
+    static bool attr_t = false;
+    if (!attr_t) {
+      DAWN_CUDA_OK(cudaFuncSetAttribute(init_conv_x3_tiled_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+      attr_t = true;
+    }
+    init_conv_x3_tiled_kernel<7><<<dim3((W + 63) / 64, (H + 7) / 8, F), 128, smem_t, st>>>(xt, F, H, W, w3, map, out, ldo);
+    DAWN_LAUNCH_OK();
+    return 0;
+  }
   const size_t smem = (size_t)ksz * ksz * 3 * Co * sizeof(float);
   static bool attr = false;
   if (!attr) {

@@ -588,7 +588,15 @@ int resblock(Ctx& c, const ResBlockW& r, const Act& x, const Act& out) {
   }
   DAWN_TRY(conv_same(c, x, r.c1, 3, y, r.st1));
   DAWN_TRY(gn_allreduce(c, r.st1));
-  if (r.cond) {
+  if (r.cond && h->use_fused_ca && gn_hcond_supported(r.co, P)) {
+    GnHcondArgs a{};
+    a.Wt = h->WT; a.T = r.T; a.ldbT = r.ldbT; a.Y = y.p; a.ldy = y.ld; a.Out = a1.p; a.ldo = a1.ld;
+    a.F = F; a.P = P; a.co = r.co;
+    a.gn_stats = h->STATS + 16 * r.st1; a.gn_count = count; a.cpg = r.co / 8;
+    a.gn_w = r.gn1w; a.gn_b = r.gn1b; a.film = r.film;
+    ProfScope ps(c, PC_GN_HCOND, 2.0 * M * 32 * r.co, 4.0 * M * (2.0 * r.co + 32));
+    DAWN_TRY(launch_gn_hcond(a, c.st));
+  } else if (r.cond) {
     // a1 = SiLU(FiLM(GN(y))) + h_cond, h_cond = Wt (M x 32) @ T_f (32 x co) per frame
     Act wt{h->WT, 32, 32, x.H, x.W};
     GemmParams p; base_params(p, wt, F);
