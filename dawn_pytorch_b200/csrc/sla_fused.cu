@@ -272,7 +272,167 @@ __global__ void __launch_bounds__(256) sla_merge_kernel(const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// out = x + bias + sum_h softmax_d(W_q,h x^) * 32^-1/2 * Bf_f[h]     (q projection, softmax over the head dim, context/out-projection)
+// One warp owns 16 pixels: q_h comes out of mma.sync as accumulator fragments, is normalised in registers and re-used as the A operand
+// of the product with the frame's composed matrix Bf_f (256 x 64, fp16 hi|lo in shared memory).  q never reaches HBM (the unfused
+// path wrote and re-read 840 MB of it per level-0 layer).
+constexpr int OCH = 128;               // pixels staged per iteration (one 16-pixel group per warp)
+constexpr int BLD = 256 + 8;           // halfs per Bf^T row
+
+__global__ void __launch_bounds__(NTH, 1) sla_out_kernel(SlaOutArgs a) {
+  extern __shared__ __align__(16) unsigned char sla_smem[];
+  __half* Wh = reinterpret_cast<__half*>(sla_smem);     // [256][LD] q weights, hi
+  __half* Wl = Wh + 256 * LD;
+  __half* Bh = Wl + 256 * LD;                           // [64 channels][BLD] Bf_f^T, hi
+  __half* Bl = Bh + C * BLD;
+  __half* Xh = Bl + C * BLD;                            // [OCH][LD]
+  __half* Xl = Xh + OCH * LD;
+  float* s_bias = reinterpret_cast<float*>(Xl + OCH * LD);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3, lm = lane >> 3, lr = lane & 7;
+  const int f = blockIdx.y;
+  const int px_lo = blockIdx.x * a.px_per_cta, px_hi = min(a.P, px_lo + a.px_per_cta);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.Wq);
+    for (int i = tid; i < 2 * 256 * C / 8; i += NTH) {
+      const int r = i / (C / 8), c8 = i - r * (C / 8);              // r in [0, 512): hi rows then lo rows
+      cp_async_16(Wh + r * LD + c8 * 8, src + i);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    const float* Bf = a.Bf + (size_t)f * 256 * a.ldb;
+    for (int i = tid; i < 256 * C; i += NTH) {
+      const int k = i >> 6, c = i & 63;
+      const float v = Bf[(size_t)k * a.ldb + c];
+      const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+      Bh[c * BLD + k] = __float2half_rn(h);
+      Bl[c * BLD + k] = __float2half_rn(v - h);
+    }
+    if (tid < C) s_bias[tid] = a.bias[tid];
+  }
+  const int l16 = tid & 15;
+  float4 xin[OCH / (NTH / 16)];
+  auto fetch = [&](int p0) {
+#pragma unroll
+    for (int i = 0; i < OCH / (NTH / 16); ++i) {
+      const int px = p0 + i * (NTH / 16) + (tid >> 4);
+      xin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (px < px_hi) xin[i] = __ldg(reinterpret_cast<const float4*>(a.x + ((size_t)f * a.P + px) * a.ldx) + l16);
+    }
+  };
+  fetch(px_lo);
+  const float qscale = a.inv_wscale * LOG2E;
+
+  for (int p0 = px_lo; p0 < px_hi; p0 += OCH) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < OCH / (NTH / 16); ++i) {
+      const int r = i * (NTH / 16) + (tid >> 4);
+      const float4 v = xin[i];
+      float s = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mu = s * (1.0f / C);
+      const float d0 = v.x - mu, d1 = v.y - mu, d2 = v.z - mu, d3 = v.w - mu;
+      float ss = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rs = 1.0f / sqrtf(ss * (1.0f / C) + 1e-5f);
+      uint32_t h0, l0, h1, l1;
+      split2h(d0 * rs, d1 * rs, h0, l0); split2h(d2 * rs, d3 * rs, h1, l1);
+      *reinterpret_cast<uint2*>(&Xh[r * LD + l16 * 4]) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(&Xl[r * LD + l16 * 4]) = make_uint2(l0, l1);
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
+    if (p0 + OCH < px_hi) fetch(p0 + OCH);
+
+    const int grp0 = p0 + warp * 16;
+    if (grp0 >= px_hi) continue;
+    uint32_t ah[4][4], al[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int aoff = (warp * 16 + (lm & 1) * 8 + lr) * LD + ks * 16 + (lm >> 1) * 8;
+      ldsm4(ah[ks], Xh + aoff);
+      ldsm4(al[ks], Xl + aoff);
+    }
+    float y[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) y[n][c] = 0.f;
+#pragma unroll 1
+    for (int head = 0; head < 8; ++head) {
+      float q[4][4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) q[n][c] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          uint32_t b[4];
+          ldsm4(b, ((lm & 2) ? Wl : Wh) + (head * 32 + n * 8 + lr) * LD + ks * 16 + (lm & 1) * 8);
+          mma3(q[n], ah[ks], al[ks], b);
+        }
+      // softmax over the 32 head dims of each row (log2 domain), times 32^-1/2
+      float m0 = -1e30f, m1 = -1e30f;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) q[n][c] *= qscale;
+        m0 = fmaxf(m0, fmaxf(q[n][0], q[n][1])); m1 = fmaxf(m1, fmaxf(q[n][2], q[n][3]));
+      }
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        q[n][0] = ex2(q[n][0] - m0); q[n][1] = ex2(q[n][1] - m0); q[n][2] = ex2(q[n][2] - m1); q[n][3] = ex2(q[n][3] - m1);
+        s0 += q[n][0] + q[n][1]; s1 += q[n][2] + q[n][3];
+      }
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      const float i0 = 0.17677669529663687f / s0, i1 = 0.17677669529663687f / s1;
+      uint32_t ph[2][4], pl[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        split2h(q[2 * ks][0] * i0, q[2 * ks][1] * i0, ph[ks][0], pl[ks][0]);
+        split2h(q[2 * ks][2] * i1, q[2 * ks][3] * i1, ph[ks][1], pl[ks][1]);
+        split2h(q[2 * ks + 1][0] * i0, q[2 * ks + 1][1] * i0, ph[ks][2], pl[ks][2]);
+        split2h(q[2 * ks + 1][2] * i1, q[2 * ks + 1][3] * i1, ph[ks][3], pl[ks][3]);
+      }
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t b[4];
+          ldsm4(b, ((lm & 2) ? Bl : Bh) + (n * 8 + lr) * BLD + head * 32 + ks * 16 + (lm & 1) * 8);
+          mma3(acc, ph[ks], pl[ks], b);
+        }
+        y[n][0] += acc[0]; y[n][1] += acc[1]; y[n][2] += acc[2]; y[n][3] += acc[3];
+      }
+    }
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const size_t row = (size_t)f * a.P + grp0 + g + 8 * hr;
+      const float* xr = a.x + row * a.ldx;
+      float* dst = a.out + row * a.ldo;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const int c = n * 8 + 2 * t;
+        const float2 r = *reinterpret_cast<const float2*>(xr + c);
+        *reinterpret_cast<float2*>(dst + c) = make_float2(r.x + s_bias[c] + y[n][2 * hr], r.y + s_bias[c + 1] + y[n][2 * hr + 1]);
+      }
+    }
+  }
+}
+
 constexpr size_t kSmem = (size_t)(2 * 512 * LD + 2 * CHUNK * LD) * 2;
+constexpr size_t kSmemOut = (size_t)(2 * 256 * LD + 2 * C * BLD + 2 * OCH * LD) * 2 + C * 4;
 
 }  // namespace
 
@@ -301,6 +461,41 @@ int launch_sla_ctx_fused(const SlaCtxArgs& a_in, const float* WoutT, float* Bf, 
   sla_merge_kernel<<<dim3(a.F, 8), 256, 0, st>>>(a.part, nsplit, WoutT, C, Bf, ldb);
   DAWN_LAUNCH_OK();
   return 0;
+}
+
+int launch_sla_out_fused(const SlaOutArgs& a_in, cudaStream_t st) {
+  SlaOutArgs a = a_in;
+  if (!sla_fused_supported(C, a.P)) { set_last_error("sla_out: unsupported shape"); return -1; }
+  static bool attr = false;
+  if (!attr) {
+    DAWN_CUDA_OK(cudaFuncSetAttribute(sla_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemOut));
+    attr = true;
+  }
+  int px = 512;
+  while (px > OCH && a.P % px != 0) px >>= 1;
+  a.px_per_cta = px;
+  sla_out_kernel<<<dim3((a.P + px - 1) / px, a.F), NTH, kSmemOut, st>>>(a);
+  DAWN_LAUNCH_OK();
+  return 0;
+}
+
+// wq: rows 0..255 of the gamma-folded to_qkv weight -> [hi|lo][256][64] fp16 with a power-of-two pre-scale
+void sla_out_pack(const float* wqkv, std::vector<uint16_t>& W, float* inv_wscale) {
+  float mx = 0.f;
+  for (size_t i = 0; i < (size_t)256 * C; ++i) mx = std::max(mx, std::fabs(wqkv[i]));
+  int e = 0;
+  if (mx > 0.f) std::frexp(mx, &e);
+  const float sc = std::ldexp(1.0f, 11 - e);
+  *inv_wscale = 1.0f / sc;
+  W.assign((size_t)2 * 256 * C, 0);
+  for (int r = 0; r < 256; ++r)
+    for (int k = 0; k < C; ++k) {
+      const float v = wqkv[(size_t)r * C + k] * sc;
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      memcpy(&W[(size_t)r * C + k], &hi, 2);
+      memcpy(&W[((size_t)256 + r) * C + k], &lo, 2);
+    }
 }
 
 // wkv: rows 256..767 of the gamma-folded to_qkv weight ([768][64]); output [hi|lo][8 heads x (k 32 | v 32)][64] fp16, power-of-two pre-scale

@@ -15,6 +15,19 @@ struct SlaCtxArgs {
   int px_per_cta;                 // set by the launcher
 };
 
+struct SlaOutArgs {
+  const float* x; int ldx;        // layer input (also the residual)
+  float* out; int ldo;            // may alias x
+  int F, P;
+  const uint16_t* Wq;             // [hi|lo][256][64] fp16 q projection, LayerNorm gain folded, pre-scaled by 1/inv_wscale
+  float inv_wscale;
+  const float* Bf; int ldb;       // [F][256][ldb] per-frame (context x out-projection) matrices
+  const float* bias;              // [64]
+  int px_per_cta;                 // set by the launcher
+};
+int launch_sla_out_fused(const SlaOutArgs& a, cudaStream_t st);
+void sla_out_pack(const float* wqkv_folded, std::vector<uint16_t>& W, float* inv_wscale);
+
 bool sla_fused_supported(int C, int P);
 size_t sla_fused_part_floats(int F, int P);
 // Bf[f][256][ldb] = per-frame (context x out-projection) matrices, as launch_sla_context produces

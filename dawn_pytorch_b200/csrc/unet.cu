@@ -123,6 +123,7 @@ struct SlaW {      // spatial linear attention (U:602-627)
   // fused context kernel (sla_fused.cu), 64-channel levels: q-only projection + K/V weights as fp16 hi|lo images
   float *Wq = nullptr, *wsum_q = nullptr, *Wq_img = nullptr; float Wq_scale = 1.f;
   uint16_t* fkv = nullptr; float f_inv_wscale = 1.f;
+  uint16_t* fq = nullptr; float fq_inv_wscale = 1.f;
 };
 struct UpW { ConvW cls[4]; };
 
@@ -410,6 +411,11 @@ int pack_sla(dawn_unet* h, const std::string& p, int C, SlaW* s) {        // p =
     float* d = nullptr;
     DAWN_TRY(dev_upload(h, tmp, &d));
     s->fkv = reinterpret_cast<uint16_t*>(d);
+    sla_out_pack(wf.data(), W, &s->fq_inv_wscale);
+    tmp.assign(W.size() / 2, 0.f);
+    memcpy(tmp.data(), W.data(), W.size() * 2);
+    DAWN_TRY(dev_upload(h, tmp, &d));
+    s->fq = reinterpret_cast<uint16_t*>(d);
   }
   std::vector<float> wt((size_t)256 * C);
   for (int c = 0; c < C; ++c)
@@ -748,17 +754,20 @@ int sla(Ctx& c, const SlaW& w, const Act& x, const std::string& name) {
                      sla_fused_part_floats(F, P) <= (size_t)(F + 2 * h->cfg.win_width) * h->lH[0] * h->lW[0] * 256;
   const int qld = fused ? 256 : 768;
   if (fused) {
-    // q only through the GEMM (softmax over the head dim in its epilogue); k, v never leave the context kernel's registers
-    GemmParams p; base_params(p, x, F);
-    p.B = w.Wq; p.Bimg = w.Wq_img; p.tc_scale = 1.0f / (kTcActScale * w.Wq_scale); p.ldb = 256; p.N = 256; p.K = x.C;
-    p.wsum = w.wsum_q; p.q_post_scale = 1.0f / sqrtf(32.0f);
-    p.Out = h->QKV; p.ldo = 256;
-    DAWN_TRY(ln_gemm(c, p, EPI_QKV_SLA, PC_QKV, x.p, x.ld, x.C, M));
+    // k, v never leave the context kernel's registers; q never leaves the output kernel's
     SlaCtxArgs a{};
     a.x = x.p; a.ldx = x.ld; a.F = F; a.P = P; a.Wkv = w.fkv; a.inv_wscale = w.f_inv_wscale; a.part = h->O;
-    ProfScope ps(c, PC_SLA_CTX, 2.0 * M * x.C * 512 + 2.0 * 8 * 32 * 32 * M + 2.0 * F * 256 * 32 * x.C, 4.0 * M * x.C);
-    h->launches++;                                     // context kernel + merge kernel
-    DAWN_TRY(launch_sla_ctx_fused(a, w.WoutT, h->BF, ldb, c.st));
+    {
+      ProfScope ps(c, PC_SLA_CTX, 2.0 * M * x.C * 512 + 2.0 * 8 * 32 * 32 * M + 2.0 * F * 256 * 32 * x.C, 4.0 * M * x.C);
+      h->launches++;                                   // context kernel + merge kernel
+      DAWN_TRY(launch_sla_ctx_fused(a, w.WoutT, h->BF, ldb, c.st));
+    }
+    SlaOutArgs o{};
+    o.x = x.p; o.ldx = x.ld; o.out = x.p; o.ldo = x.ld; o.F = F; o.P = P; o.Wq = w.fq; o.inv_wscale = w.fq_inv_wscale;
+    o.Bf = h->BF; o.ldb = ldb; o.bias = w.bout;
+    ProfScope ps2(c, PC_OUTPROJ, 2.0 * M * x.C * 256 + 2.0 * M * 256 * x.C, 8.0 * M * x.C);
+    DAWN_TRY(launch_sla_out_fused(o, c.st));
+    return tap(c, name, x);
   } else {
     GemmParams p; base_params(p, x, F);
     p.B = w.Wqkv; p.Bimg = w.Wqkv_img; p.tc_scale = 1.0f / (kTcActScale * w.Wqkv_scale); p.ldb = 768; p.N = 768; p.K = x.C;
