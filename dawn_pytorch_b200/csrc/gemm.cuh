@@ -20,6 +20,8 @@ enum Epi : int {
 struct GemmParams {
   // A operand (gathered)
   const float* A; int lda; int Cin;
+  // optional pre-split copy of A (fp16 hi and lo planes, dense rows of Cin halfs): the tcgen05 producers then only copy
+  const unsigned short* A16h = nullptr; const unsigned short* A16l = nullptr;
   int IH, IW;              // input frame dims
   int OHs, OWs;            // output sub-grid dims; rows m = (f, i, j)
   int in_stride;           // input pixel = (i*in_stride + dy, j*in_stride + dx)

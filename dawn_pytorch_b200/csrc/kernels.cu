@@ -1,4 +1,6 @@
 // Non-GEMM kernels of the DAWN denoising UNet: norms, conditioning tables, attention cores, layout.
+#include <cuda_fp16.h>
+#include <algorithm>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -252,6 +254,34 @@ __global__ void ca_rstd_kernel(const float* __restrict__ gates, const float* __r
 int launch_ca_rstd(const float* gates, const float* G, int M, int P, float* Wt, cudaStream_t st) {
   const long long n = (long long)M * 4;
   ca_rstd_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(gates, G, M, P, Wt);
+  DAWN_LAUNCH_OK();
+  return 0;
+}
+
+// =========================================================================== fp16 hi | lo copy of an activation
+// x (M rows, C channels, row stride ld) -> dense hi[M][C], lo[M][C]: the same 11-bit split the tcgen05 producers apply on the fly
+__global__ void split_rows_kernel(const float* __restrict__ x, int ld, int C, long long M, uint2* __restrict__ hi,
+                                  uint2* __restrict__ lo) {
+  const int c4n = C >> 2;
+  const long long total = M * c4n;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / c4n;
+    const int c4 = (int)(idx - row * c4n);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)row * ld) + c4);
+    const float h0 = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
+    const float h1 = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
+    const float h2 = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
+    const float h3 = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
+    const __half2 a = __floats2half2_rn(h0, h1), b = __floats2half2_rn(h2, h3);
+    const __half2 c = __floats2half2_rn(v.x - h0, v.y - h1), d = __floats2half2_rn(v.z - h2, v.w - h3);
+    hi[idx] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    lo[idx] = make_uint2(*reinterpret_cast<const uint32_t*>(&c), *reinterpret_cast<const uint32_t*>(&d));
+  }
+}
+int launch_split_rows(const float* x, int ld, int C, long long M, void* hi, void* lo, cudaStream_t st) {
+  const long long total = M * (C >> 2);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+  split_rows_kernel<<<blocks, 256, 0, st>>>(x, ld, C, M, (uint2*)hi, (uint2*)lo);
   DAWN_LAUNCH_OK();
   return 0;
 }

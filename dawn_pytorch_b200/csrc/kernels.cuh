@@ -73,6 +73,7 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t st);       // tensor-cor
 
 // spatial linear attention: per (frame, head) context + composed out-projection  U:618-626
 //   Bf[f][h*32+d][c] = sum_e ctx[f,h][d][e] * WoutT[h*32+e][c]
+int launch_split_rows(const float* x, int ld, int C, long long M, void* hi, void* lo, cudaStream_t st);
 int launch_sla_context(const float* qkv, int ld, int F, int P, const float* WoutT /*[256][C]*/, int C,
                        float* Bf, int ldb, cudaStream_t st);
 

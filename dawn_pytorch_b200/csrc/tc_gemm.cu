@@ -198,6 +198,34 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
       ++it;
     };
 
+    // Pre-split A (fp16 hi | lo planes written by split_rows_kernel): the panel rows are copied global -> shared with cp.async, no
+    // register staging and no conversion.  Each thread's copies of a stage signal a_full through cp.async.mbarrier.arrive.noinc, so
+    // the producers run up to STAGES panels ahead.  Used where one A panel feeds several n-tiles and the conversion was the
+    // bottleneck (the 8x8-level 3x3 convolutions: 4 n-tiles, producers at ~4.5k cycles per panel against ~0.85k of MMA issue).
+    if (p.A16h != nullptr) {
+      for (int gi = 0; gi < n_items; ++gi, ++it) {
+        const int T = gi / KC, kc = gi - T * KC;
+        ensure_table(T);
+        const RowInfo* rows = s_rows[T % 3];
+        const int tap = kc / chunks_per_tap;
+        const int c0 = (kc - tap * chunks_per_tap) * BKP;
+        const int dy = p.dy[tap], dx = p.dx[tap];
+        const int s = it % STAGES;
+        mbar_wait(&slot_free[s], ((it / STAGES) & 1) ^ 1);
+        const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_PANEL;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const RowInfo ri = rows[r0 + 32 * q];
+          const int iy = ri.iy + dy, ix = ri.ix + dx;
+          const bool ok = (ri.pix >= 0) && (iy >= 0) && (iy < p.IH) && (ix >= 0) && (ix < p.IW);
+          const size_t e = ok ? (size_t)(ri.pix + iy * p.IW + ix) * p.Cin + c0 + 8 * c16 : 0;
+          const uint32_t off = swz(r0 + 32 * q, c16), nbytes = ok ? 16u : 0u;        // src-size 0: zero fill
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_hi + off), "l"(p.A16h + e), "r"(nbytes) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_lo + off), "l"(p.A16l + e), "r"(nbytes) : "memory");
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&a_full[s])) : "memory");
+      }
+    } else
     // global loads run ahead of the split/store in statically indexed register buffers:
     // two items ahead (3 buffers) for BN = 64, one item ahead (2 buffers) for BN = 128 (96-register budget)
     if constexpr (BN == 64) {

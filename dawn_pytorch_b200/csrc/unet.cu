@@ -141,6 +141,7 @@ struct dawn_unet {
   bool committed = false;
   bool use_tc = true;                          // tcgen05 contraction path (DAWN_TC=0 falls back to mma.sync)
   bool use_conv3 = true;                       // halo-tile tcgen05 3x3 conv (DAWN_TC_CONV3=0 falls back to the per-tap GEMM)
+  bool use_presplit = true;                    // fp16 hi|lo pre-split of A for multi-n-tile 3x3 convs (DAWN_PRESPLIT=0: off)
   bool use_fused_ca = true;                    // fused cross-attention gate kernel for ci <= 128 (DAWN_FUSED_CA=0: unfused)
   bool use_fused_sla = true;                   // fused SLA context on 64-channel levels (DAWN_FUSED_SLA=0: unfused)
   bool use_fused_ta = true;                    // fused per-pixel temporal attention on 64-channel levels (DAWN_FUSED_TA=0: unfused)
@@ -531,7 +532,21 @@ int Ctx::gemm(const GemmParams& p, int epi, int cat) {
   if (epi == EPI_CA_GATE) bytes = 4.0 * p.M * (p.Cin + 24.0);
   ProfScope ps(*this, cat, flops, bytes);
   if (h->use_tc && h->use_conv3 && p.Bimg != nullptr && tc_conv3_supported(p, epi)) return launch_tc_conv3(p, p.Bimg, st);
-  if (h->use_tc && p.Bimg != nullptr && tc_gemm_supported(p, epi)) return launch_tc_gemm(p, p.Bimg, epi, st);
+  if (h->use_tc && p.Bimg != nullptr && tc_gemm_supported(p, epi)) {
+    // several n-tiles re-convert the same A panels (per-tap gather of the small levels' 3x3 convolutions): split once instead
+    const long long in_rows = (long long)(p.M / (p.OHs * p.OWs)) * p.IH * p.IW;
+    const size_t need = (size_t)in_rows * p.Cin * 4;                                   // two fp16 planes
+    const size_t have = (size_t)(h->F + 2 * h->cfg.win_width) * h->lH[0] * h->lW[0] * 256 * sizeof(float);
+    if (h->use_presplit && p.ntaps == 9 && p.N >= 256 && !p.perm_in && p.Cin % 64 == 0 && need <= have) {
+      GemmParams q = p;
+      unsigned short* hi = reinterpret_cast<unsigned short*>(h->O);
+      q.A16h = hi; q.A16l = hi + (size_t)in_rows * p.Cin;
+      h->launches++;
+      DAWN_TRY(launch_split_rows(p.A, p.lda, p.Cin, in_rows, (void*)q.A16h, (void*)q.A16l, st));
+      return launch_tc_gemm(q, q.Bimg, epi, st);
+    }
+    return launch_tc_gemm(p, p.Bimg, epi, st);
+  }
   return launch_gemm(p, epi, st);
 }
 
@@ -953,6 +968,7 @@ int dawn_unet_create(const dawn_unet_cfg* cfg, dawn_unet** out) {
   { const char* e = getenv("DAWN_FUSED_TA"); h->use_fused_ta = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_FUSED_SLA"); h->use_fused_sla = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_FUSED_CA"); h->use_fused_ca = !(e && e[0] == '0'); }
+  { const char* e = getenv("DAWN_PRESPLIT"); h->use_presplit = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_TC_CONV3"); h->use_conv3 = !(e && e[0] == '0'); }
   h->nlev = cfg->n_levels;
   h->dims.push_back(cfg->dim);
