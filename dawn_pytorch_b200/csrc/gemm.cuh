@@ -22,6 +22,7 @@ struct GemmParams {
   const float* A; int lda; int Cin;
   // optional pre-split copy of A (fp16 hi and lo planes, dense rows of Cin halfs): the tcgen05 producers then only copy
   const unsigned short* A16h = nullptr; const unsigned short* A16l = nullptr;
+  int want_split = 0;      // host side: ask Ctx::gemm to build the pre-split copy
   int IH, IW;              // input frame dims
   int OHs, OWs;            // output sub-grid dims; rows m = (f, i, j)
   int in_stride;           // input pixel = (i*in_stride + dy, j*in_stride + dx)

@@ -537,7 +537,7 @@ int Ctx::gemm(const GemmParams& p, int epi, int cat) {
     const long long in_rows = (long long)(p.M / (p.OHs * p.OWs)) * p.IH * p.IW;
     const size_t need = (size_t)in_rows * p.Cin * 4;                                   // two fp16 planes
     const size_t have = (size_t)(h->F + 2 * h->cfg.win_width) * h->lH[0] * h->lW[0] * 256 * sizeof(float);
-    if (h->use_presplit && p.ntaps == 9 && p.N >= 256 && !p.perm_in && p.Cin % 64 == 0 && need <= have) {
+    if (h->use_presplit && ((p.ntaps == 9 && p.N >= 256 && !p.perm_in) || p.want_split) && p.Cin % 64 == 0 && need <= have) {
       GemmParams q = p;
       unsigned short* hi = reinterpret_cast<unsigned short*>(h->O);
       q.A16h = hi; q.A16l = hi + (size_t)in_rows * p.Cin;
@@ -557,7 +557,14 @@ int tap(Ctx& c, const std::string& name, const Act& a);
 int ln_gemm(Ctx& c, GemmParams& p, int epi, int cat, const float* x, int ldx, int C, int rows) {
   dawn_unet* h = c.h;
   p.ln_inline = 0; p.rowstats = h->ROWSTATS;
-  if (h->use_tc && p.Bimg != nullptr && tc_gemm_supported(p, epi) && p.ntaps == 1) {
+  const bool tc_ok = h->use_tc && p.Bimg != nullptr && tc_gemm_supported(p, epi) && p.ntaps == 1;
+  if (tc_ok && h->use_presplit && p.N >= 384 && p.Cin % 64 == 0) {
+    // N = 768 is six 128-column tiles, each re-gathering and re-splitting the same A panels: split once (cp.async producers),
+    // row statistics from the stand-alone kernel
+    p.want_split = 1;
+    ProfScope ps(c, PC_ROWSTATS, 0, 4.0 * rows * C);
+    DAWN_TRY(launch_rowstats(x, ldx, C, rows, 1e-5f, h->ROWSTATS, c.st));
+  } else if (tc_ok) {
     p.ln_inline = 1; p.rowstats = nullptr;
   } else {
     ProfScope ps(c, PC_ROWSTATS, 0, 4.0 * rows * C);
