@@ -107,9 +107,9 @@ int launch_gn_apply(const float* Y, int ldy, int C, int M, const double* stats, 
 // =========================================================================== small dense layers (per frame GEMV)
 // one warp per output; grid (ceil(Nout/8), F).  act: 1 = SiLU on the input
 template <int ACT>
-__global__ void frame_linear_kernel(const float* __restrict__ x, int ldx, int off, int K,
-                                    const float* __restrict__ W, const float* __restrict__ b, int Nout,
-                                    float* __restrict__ out) {
+__device__ __forceinline__ void frame_linear_body(const float* __restrict__ x, int ldx, int off, int K,
+                                                  const float* __restrict__ W, const float* __restrict__ b, int Nout,
+                                                  float* __restrict__ out) {
   extern __shared__ float sx[];
   const int f = blockIdx.y;
   for (int i = threadIdx.x; i < K; i += blockDim.x) {
@@ -125,6 +125,22 @@ __global__ void frame_linear_kernel(const float* __restrict__ x, int ldx, int of
   for (int i = lane; i < K; i += 32) acc += w[i] * sx[i];
   acc = warp_sum(acc);
   if (lane == 0) out[(size_t)f * Nout + j] = acc + (b ? b[j] : 0.f);
+}
+template <int ACT>
+__global__ void frame_linear_kernel(const float* __restrict__ x, int ldx, int off, int K,
+                                    const float* __restrict__ W, const float* __restrict__ b, int Nout,
+                                    float* __restrict__ out) {
+  frame_linear_body<ACT>(x, ldx, off, K, W, b, Nout, out);
+}
+// all (block, cross-attention) pairs of the per-clip conditioning in one launch each: blockIdx.z = descriptor
+__global__ void cond_mlp_batched_kernel(const float* __restrict__ cond, int cond_ld, const CondDesc* __restrict__ descs) {
+  const CondDesc d = descs[blockIdx.z];
+  if ((int)blockIdx.x * 8 >= d.n1) return;
+  frame_linear_body<1>(cond, cond_ld, d.off, d.K, d.mW, d.mB, d.n1, d.ctx);
+}
+__global__ void cond_kv_batched_kernel(const CondDesc* __restrict__ descs) {
+  const CondDesc d = descs[blockIdx.z];
+  frame_linear_body<0>(d.ctx, d.n1, 0, d.n1, d.Wkv, nullptr, 128, d.kv);
 }
 
 int launch_cond_mlp(const float* cond, int cond_ld, int off, int K, const float* W, const float* b, int Nout,
@@ -146,13 +162,12 @@ int launch_linear_nobias(const float* x, int K, const float* W, int Nout, int F,
 //   o_h = nv + w_h (v_h - nv),  so  to_out(o) = u_0 + sum_h w_h u_h  with per-frame vectors
 //   u_0 = Wout * rep(nv),  u_h = Wout[:, h] (v_h - nv)   (U:530-559).
 // The output LayerNorm (U:511-514) of that combination needs only the centred vectors and their Gram matrix.
-__global__ void ca_tables_kernel(CaTableArgs a) {
+__device__ __forceinline__ void ca_tables_body(const CaTableArgs& a, int f) {
   extern __shared__ float sm[];
   float* u = sm;                       // [9][co]
   __shared__ float s_kv[128];
   __shared__ float s_red[9];
   __shared__ float s_nk[8], s_nv[8];
-  const int f = blockIdx.x;
   const int tid = threadIdx.x;
   const int co = a.co;
   if (tid < 128) s_kv[tid] = a.kv[(size_t)f * 128 + tid];
@@ -212,6 +227,29 @@ __global__ void ca_tables_kernel(CaTableArgs a) {
     const int r = idx / co, c = idx - r * co;
     T[(size_t)r * a.ldbT + c] = u[idx] * a.gout[c];
   }
+}
+
+__global__ void ca_tables_kernel(CaTableArgs a) { ca_tables_body(a, blockIdx.x); }
+__global__ void ca_tables_batched_kernel(const CondDesc* __restrict__ descs) { ca_tables_body(descs[blockIdx.y].t, blockIdx.x); }
+
+int launch_cond_batched(const float* cond, int cond_ld, const CondDesc* descs_dev, int ndesc, int max_n1, int max_k, int max_co, int F,
+                        cudaStream_t st) {
+  static size_t attr = 0;
+  const size_t smem_kv = (size_t)max_n1 * sizeof(float), smem_t = (size_t)9 * max_co * sizeof(float);
+  if (smem_kv > 48 * 1024 || smem_t > 48 * 1024) {
+    if (std::max(smem_kv, smem_t) > attr) {
+      DAWN_CUDA_OK(cudaFuncSetAttribute(cond_kv_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem_kv, smem_t)));
+      DAWN_CUDA_OK(cudaFuncSetAttribute(ca_tables_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem_kv, smem_t)));
+      attr = std::max(smem_kv, smem_t);
+    }
+  }
+  cond_mlp_batched_kernel<<<dim3((max_n1 + 7) / 8, F, ndesc), 256, (size_t)max_k * sizeof(float), st>>>(cond, cond_ld, descs_dev);
+  DAWN_LAUNCH_OK();
+  cond_kv_batched_kernel<<<dim3(16, F, ndesc), 256, smem_kv, st>>>(descs_dev);
+  DAWN_LAUNCH_OK();
+  ca_tables_batched_kernel<<<dim3(F, ndesc), 256, smem_t, st>>>(descs_dev);
+  DAWN_LAUNCH_OK();
+  return 0;
 }
 
 int launch_ca_tables(const CaTableArgs& a, int F, cudaStream_t st) {

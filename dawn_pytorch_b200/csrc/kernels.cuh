@@ -34,6 +34,16 @@ struct CaTableArgs {
   float* T;            // [F][32][ldbT]
   float* G;            // [F][3][81]
 };
+// one (conditioned block, cross-attention) pair of the per-clip conditioning pipeline: cond slice -> MLP -> (k | v) -> tables
+struct CondDesc {
+  const float* mW; const float* mB; int off, K, n1;   // Linear(SiLU(cond[:, off:off+K])) -> n1 = 2*co features
+  const float* Wkv;                                   // [128][n1]
+  float* ctx; float* kv;                              // scratch [F][n1], [F][128]
+  CaTableArgs t;
+};
+int launch_cond_batched(const float* cond, int cond_ld, const CondDesc* descs_dev, int ndesc, int max_n1, int max_k, int max_co, int F,
+                        cudaStream_t st);
+
 int launch_ca_tables(const CaTableArgs& a, int F, cudaStream_t st);
 
 // Wt[m][ca*9 + {0, 1+h}] = rstd_ca(m) * {1, gate(m,ca,h)}           U:511-514 (to_out LayerNorm) via Gram form

@@ -165,6 +165,7 @@ struct dawn_unet {
   std::vector<UpW> up_conv;
   float *headW[2] = {nullptr, nullptr}, *headB[2] = {nullptr, nullptr};
   FilmDesc* film_descs = nullptr; int n_film = 0;
+  CondDesc* cond_descs = nullptr; int n_cond = 0, cond_max_n1 = 0, cond_max_k = 0, cond_max_co = 0;   // batched per-clip prep
 
   // workspace (per set_num_frames)
   int F = 0, H = 0, W = 0;
@@ -861,6 +862,11 @@ int tap(Ctx& c, const std::string& name, const Act& a) {
 int prep_cond(dawn_unet* h, const float* cond, cudaStream_t st) {
   const int F = h->F;
   Ctx c{h, st};
+  if (h->n_cond > 0 && !h->prof_on) {
+    // three launches for all (block, cross-attention) pairs; the per-pair path below is kept for profiling
+    h->launches += 3;
+    return launch_cond_batched(cond, h->cond_dim, h->cond_descs, h->n_cond, h->cond_max_n1, h->cond_max_k, h->cond_max_co, F, st);
+  }
   const int off[3] = {h->cfg.cond_aud, 0, h->cfg.cond_aud + h->cfg.cond_pose};          // pose, aud, eye slices (U:425-428)
   const int kd[3] = {h->cfg.cond_pose, h->cfg.cond_aud, h->cfg.cond_eye};
   for (auto& r : h->rb) {
@@ -1155,6 +1161,29 @@ int dawn_unet_set_num_frames(dawn_unet* h, int F, int height, int width) {
     float* d; DAWN_TRY(dev_alloc(own, descs.size() * sizeof(FilmDesc) / sizeof(float) + 4, &d, cnt));
     DAWN_CUDA_OK(cudaMemcpy(d, descs.data(), descs.size() * sizeof(FilmDesc), cudaMemcpyHostToDevice));
     h->film_descs = (FilmDesc*)d; h->n_film = (int)descs.size();
+  }
+  {
+    // descriptors of the per-clip conditioning pipeline: one per (conditioned block, cross-attention), own scratch each
+    const int off[3] = {h->cfg.cond_aud, 0, h->cfg.cond_aud + h->cfg.cond_pose};          // pose, aud, eye slices (U:425-428)
+    const int kd[3] = {h->cfg.cond_pose, h->cfg.cond_aud, h->cfg.cond_eye};
+    std::vector<CondDesc> cd;
+    h->cond_max_n1 = h->cond_max_k = h->cond_max_co = 0;
+    for (auto& r : h->rb) {
+      if (!r.cond) continue;
+      for (int a = 0; a < 3; ++a) {
+        CondDesc d{};
+        d.mW = r.mW[a]; d.mB = r.mB[a]; d.off = off[a]; d.K = kd[a]; d.n1 = 2 * r.co; d.Wkv = r.ca[a].Wkv;
+        DAWN_TRY(dev_alloc(own, (size_t)F * d.n1, &d.ctx, cnt));
+        DAWN_TRY(dev_alloc(own, (size_t)F * 128, &d.kv, cnt));
+        d.t.kv = d.kv; d.t.nkv = r.ca[a].nkv; d.t.qs = r.ca[a].qs; d.t.ks = r.ca[a].ks; d.t.Wout = r.ca[a].Wout; d.t.gout = r.ca[a].gout;
+        d.t.co = r.co; d.t.ldbT = r.ldbT; d.t.ca = a; d.t.kq = r.kq; d.t.nkq = r.nkq; d.t.T = r.T; d.t.G = r.G;
+        cd.push_back(d);
+        h->cond_max_n1 = std::max(h->cond_max_n1, d.n1); h->cond_max_k = std::max(h->cond_max_k, d.K); h->cond_max_co = std::max(h->cond_max_co, r.co);
+      }
+    }
+    float* d; DAWN_TRY(dev_alloc(own, cd.size() * sizeof(CondDesc) / sizeof(float) + 4, &d, cnt));
+    DAWN_CUDA_OK(cudaMemcpy(d, cd.data(), cd.size() * sizeof(CondDesc), cudaMemcpyHostToDevice));
+    h->cond_descs = (CondDesc*)d; h->n_cond = (int)cd.size();
   }
   h->sh_nranks = 1; h->sh_rank = 0; h->sh_Fglobal = F; h->sh_halo_l = 0; h->sh_halo_r = 0;   // a new geometry is unsharded until init_shard
   DAWN_TRY(launch_rotary_table(h->rot_freqs, F, 0, h->ROT, 0));
