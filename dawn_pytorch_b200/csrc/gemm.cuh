@@ -23,6 +23,7 @@ struct GemmParams {
   // optional pre-split copy of A (fp16 hi and lo planes, dense rows of Cin halfs): the tcgen05 producers then only copy
   const unsigned short* A16h = nullptr; const unsigned short* A16l = nullptr;
   int want_split = 0;      // host side: ask Ctx::gemm to build the pre-split copy
+  int up2 = 0;             // halo conv3 kernel only: 64-column block j of the output is parity class j of a 2x upsampled grid
   int IH, IW;              // input frame dims
   int OHs, OWs;            // output sub-grid dims; rows m = (f, i, j)
   int in_stride;           // input pixel = (i*in_stride + dy, j*in_stride + dx)

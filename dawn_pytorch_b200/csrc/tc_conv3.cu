@@ -246,7 +246,14 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
       for (int i = 0; i < 64; ++i) acc[i] *= p.tc_scale;
       const int oy = y0 + (row_in_tile >> 3), ox = x0 + (row_in_tile & 7);
       const bool rv = (oy < H) && (ox < W);
-      const size_t opix = (size_t)f * H * W + (size_t)(rv ? oy * W + ox : 0);
+      size_t opix = (size_t)f * H * W + (size_t)(rv ? oy * W + ox : 0);
+      int ocol = n0;
+      if (p.up2) {
+        // transposed conv as one 3x3 conv with 4 x 64 output columns: column block = output parity class (py, px)
+        const int cls = n0 >> 6, py = cls >> 1, px = cls & 1;
+        opix = (size_t)f * 4 * H * W + (size_t)(rv ? (2 * oy + py) * 2 * W + 2 * ox + px : 0);
+        ocol = n0 & 63;
+      }
       if (p.bias) {
         const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
@@ -255,7 +262,7 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
           acc[4 * i] += b.x; acc[4 * i + 1] += b.y; acc[4 * i + 2] += b.z; acc[4 * i + 3] += b.w;
         }
       }
-      store_rows_coalesced(wbuf, acc, p.Out, opix, p.ldo, n0, rv, lane);
+      store_rows_coalesced(wbuf, acc, p.Out, opix, p.ldo, ocol, rv, lane);
       if (p.stats != nullptr) {
         if (etid < 16) s_st[etid] = 0.f;
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
@@ -323,6 +330,7 @@ bool tc_conv3_supported(const GemmParams& p, int epi) {
   if (p.b_batch_stride != 0 || p.rows_per_batch != p.M) return false;
   if ((p.lda & 3) || (p.ldo & 3)) return false;
   if (p.stats && (p.cpg % 8 != 0)) return false;
+  if (p.up2 && (p.stats != nullptr || p.N != 256)) return false;
   return true;
 }
 

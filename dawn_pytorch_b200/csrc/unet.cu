@@ -125,7 +125,7 @@ struct SlaW {      // spatial linear attention (U:602-627)
   uint16_t* fkv = nullptr; float f_inv_wscale = 1.f;
   uint16_t* fq = nullptr; float fq_inv_wscale = 1.f;
 };
-struct UpW { ConvW cls[4]; };
+struct UpW { ConvW cls[4]; ConvW all; };      // all: the four parity classes as one 3x3 conv with 4*C outputs (C = 64)
 
 }  // namespace dawn
 
@@ -457,6 +457,29 @@ int pack_up(dawn_unet* h, const std::string& name, int C, UpW* u) {
       DAWN_TRY(upload_tc_image(h, m, 4 * C, C, ldb, &cw.img, &cw.img_scale));
       cw.b = bdev; cw.K = 4 * C; cw.N = C; cw.ldb = ldb;
     }
+  if (C == 64) {
+    // one 3x3 conv over the input grid producing all four output parities: weight rows (tap, cin), columns (class, cout);
+    // taps a class does not touch stay zero (2.25x the MACs, one launch of the halo-tile kernel instead of four gather GEMMs)
+    const int N4 = 4 * C;
+    std::vector<float> m((size_t)9 * C * N4, 0.f), b4(N4, 0.f);
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const int cls = py * 2 + px;
+        for (int n = 0; n < C; ++n) b4[cls * C + n] = b->data[n];
+        for (int ty = 0; ty < 2; ++ty)
+          for (int tx = 0; tx < 2; ++tx) {
+            const int ky = kUpK[py][ty], kx = kUpK[px][tx];
+            const int tap = (kUpD[py][ty] + 1) * 3 + (kUpD[px][tx] + 1);
+            for (int c = 0; c < C; ++c)
+              for (int n = 0; n < C; ++n)
+                m[((size_t)tap * C + c) * N4 + cls * C + n] = w->data[(((size_t)c * C + n) * 4 + ky) * 4 + kx];
+          }
+      }
+    DAWN_TRY(dev_upload(h, m, &u->all.w));
+    DAWN_TRY(upload_tc_image(h, m, 9 * C, N4, N4, &u->all.img, &u->all.img_scale));
+    DAWN_TRY(dev_upload(h, b4, &u->all.b));
+    u->all.K = 9 * C; u->all.N = N4; u->all.ldb = N4;
+  }
   return 0;
 }
 
@@ -559,7 +582,7 @@ int ln_gemm(Ctx& c, GemmParams& p, int epi, int cat, const float* x, int ldx, in
   dawn_unet* h = c.h;
   p.ln_inline = 0; p.rowstats = h->ROWSTATS;
   const bool tc_ok = h->use_tc && p.Bimg != nullptr && tc_gemm_supported(p, epi) && p.ntaps == 1;
-  if (tc_ok && h->use_presplit && p.N >= 384 && p.Cin % 64 == 0) {
+  if (tc_ok && h->use_presplit && (p.N >= 384 || (p.N == 192 && p.Cin >= 256)) && p.Cin % 64 == 0) {
     // N = 768 is six 128-column tiles, each re-gathering and re-splitting the same A panels: split once (cp.async producers),
     // row statistics from the stand-alone kernel
     p.want_split = 1;
@@ -828,6 +851,16 @@ int downsample(Ctx& c, const ConvW& w, const Act& x, const Act& out, const std::
 }
 
 int upsample(Ctx& c, const UpW& u, const Act& x, const Act& out, const std::string& name) {       // U:165-167
+  if (c.h->use_tc && c.h->use_conv3 && u.all.img != nullptr) {
+    GemmParams p; base_params(p, x, c.h->F);
+    set_weights(p, u.all); set_square_taps(p, 3, 1);
+    p.up2 = 1; p.Out = out.p; p.ldo = out.ld;
+    if (tc_conv3_supported(p, EPI_PLAIN)) {
+      ProfScope ps(c, PC_CONV_OTHER, 2.0 * p.M * 4.0 * x.C * x.C * 4, 4.0 * p.M * (x.C + 4.0 * x.C));
+      DAWN_TRY(launch_tc_conv3(p, p.Bimg, c.st));
+      return tap(c, name, out);
+    }
+  }
   for (int py = 0; py < 2; ++py)
     for (int px = 0; px < 2; ++px) {
       GemmParams p; base_params(p, x, c.h->F);
