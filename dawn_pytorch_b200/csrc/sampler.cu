@@ -2,7 +2,14 @@
 // 0.9-quantile of |x0| over the whole clip (torch.quantile semantics, linear interpolation), and the eta-noise update.
 // Everything stays on the device: no host synchronisation inside a sampling step.
 #include "common.cuh"
+#include "sampler.cuh"
 #include "../../include/dawn_unet.h"
+
+#define DAWN_TRY(expr)         \
+  do {                         \
+    int _rc = (expr);          \
+    if (_rc != 0) return _rc;  \
+  } while (0)
 
 namespace dawn {
 namespace {
@@ -12,6 +19,16 @@ __global__ void x0_abs_kernel(const float* __restrict__ x, const float* __restri
                               uint32_t* __restrict__ keys) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     keys[i] = __float_as_uint(fabsf(ca * x[i] - cb * eps[i]));
+}
+
+// one launch instead of a pageable-host memcpy + three memsets (keeps the step capturable in a CUDA graph)
+__global__ void select_init_kernel(uint32_t* state, unsigned int* hist, unsigned long long* count_le, unsigned int* min_gt,
+                                   unsigned long long lo) {
+  hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    state[0] = 0u; state[1] = 0u; state[2] = (uint32_t)(lo & 0xFFFFFFFFull); state[3] = (uint32_t)(lo >> 32);
+    *count_le = 0ull; *min_gt = 0xFFFFFFFFu;
+  }
 }
 
 // state[0] = prefix value, state[1] = prefix mask, state[2..3] = remaining rank (64-bit), hist[256]
@@ -93,20 +110,15 @@ __global__ void ddim_update_kernel(float* __restrict__ x, const float* __restric
 }
 
 }  // namespace
-}  // namespace dawn
 
-using namespace dawn;
-
-extern "C" {
-
-// One DDIM update in place on x (device, n floats = one clip's (3, F, h, w) latent):
-//   x0 = ca*x - cb*eps;  s = max(1, quantile_q(|x0|)) if q > 0 else 1;  x0 = clamp(x0,-s,s)/s;
-//   x = x0*sqrt_an + c*eps + sigma*noise      (noise may be NULL: last step, U:1201)
-// scratch: device buffer of at least n + 512 32-bit words (256-byte aligned).  Stream-ordered, no host sync.
-int dawn_ddim_step(float* x, const float* eps, const float* noise, int64_t n, float ca, float cb, float sqrt_an, float c,
-                   float sigma, float q, void* scratch, void* stream) {
-  if (!x || !eps || !scratch || n <= 0) { set_last_error("dawn_ddim_step: bad argument"); return -1; }
-  cudaStream_t st = (cudaStream_t)stream;
+// One DDIM update in place on x (n_local floats of this rank's frames of the (3, F, h, w) latent).  The dynamic threshold
+// is the q-quantile of |x0| over the n_global values of the WHOLE clip: with a frame-sharded clip every rank histograms
+// its own keys and the 256-bin digit histograms (4 passes), the count <= v and the min key above v are all-reduced through
+// `red`, so every rank walks the identical radix-select and ends with the bit-identical threshold.
+int ddim_step_impl(float* x, const float* eps, const float* noise, int64_t n_local, int64_t n_global, float ca, float cb,
+                   float sqrt_an, float c, float sigma, float q, void* scratch, cudaStream_t st, const DdimReduce* red) {
+  if (!x || !eps || !scratch || n_local <= 0 || n_global < n_local) { set_last_error("dawn_ddim_step: bad argument"); return -1; }
+  const long long n = n_local;
   const int threads = 256;
   int blocks = (int)std::min<long long>((n + threads - 1) / threads, 148LL * 8);
   float* s_ptr = nullptr;
@@ -120,26 +132,39 @@ int dawn_ddim_step(float* x, const float* eps, const float* noise, int64_t n, fl
     float* s_out = (float*)(base + 263);
     uint32_t* keys = base + 512;
     // torch.quantile: ranks = q * (n - 1) evaluated in fp32 (ATen quantile_compute), lerp between floor and ceil
-    const float rank_f = q * (float)(n - 1);
+    const float rank_f = q * (float)(n_global - 1);
     const long long lo = (long long)floorf(rank_f), hi = (long long)ceilf(rank_f);
     const float w = rank_f - floorf(rank_f);
+    select_init_kernel<<<1, 256, 0, st>>>(state, hist, count_le, min_gt, (unsigned long long)lo);
     x0_abs_kernel<<<blocks, threads, 0, st>>>(x, eps, ca, cb, n, keys);
-    const uint32_t init[4] = {0u, 0u, (uint32_t)((unsigned long long)lo & 0xFFFFFFFFu), (uint32_t)((unsigned long long)lo >> 32)};
-    DAWN_CUDA_OK(cudaMemcpyAsync(state, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    DAWN_CUDA_OK(cudaMemsetAsync(hist, 0, 256 * sizeof(unsigned int), st));
     for (int shift = 24; shift >= 0; shift -= 8) {
       radix_hist_kernel<<<blocks, 256, 0, st>>>(keys, n, state, shift, hist);
+      if (red) DAWN_TRY(red->sum_u32(red->ctx, hist, 256, st));
       radix_pick_kernel<<<1, 32, 0, st>>>(state, shift, hist);
     }
-    DAWN_CUDA_OK(cudaMemsetAsync(count_le, 0, sizeof(unsigned long long), st));
-    DAWN_CUDA_OK(cudaMemsetAsync(min_gt, 0xFF, sizeof(unsigned int), st));
     next_stat_kernel<<<blocks, threads, 0, st>>>(keys, n, state, count_le, min_gt);
+    if (red) {
+      DAWN_TRY(red->sum_u64(red->ctx, count_le, 1, st));
+      DAWN_TRY(red->min_u32(red->ctx, min_gt, 1, st));
+    }
     threshold_kernel<<<1, 1, 0, st>>>(state, count_le, min_gt, lo, hi, w, s_out);
     s_ptr = s_out;
   }
   ddim_update_kernel<<<blocks, threads, 0, st>>>(x, eps, noise, s_ptr, ca, cb, sqrt_an, c, sigma, n);
   DAWN_LAUNCH_OK();
   return 0;
+}
+
+}  // namespace dawn
+
+using namespace dawn;
+
+extern "C" {
+
+// single-GPU entry (see include/dawn_unet.h); dawn_unet_ddim_step in unet.cu is the frame-sharded one
+int dawn_ddim_step(float* x, const float* eps, const float* noise, int64_t n, float ca, float cb, float sqrt_an, float c,
+                   float sigma, float q, void* scratch, void* stream) {
+  return ddim_step_impl(x, eps, noise, n, n, ca, cb, sqrt_an, c, sigma, q, scratch, (cudaStream_t)stream, nullptr);
 }
 
 }  // extern "C"

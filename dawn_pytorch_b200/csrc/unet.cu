@@ -18,6 +18,7 @@
 #include "temporal_fused.cuh"
 #include "sla_fused.cuh"
 #include "ca_fused.cuh"
+#include "sampler.cuh"
 
 namespace dawn {
 
@@ -52,7 +53,7 @@ struct NcclApi {
   const char* (*GetErrorString)(int) = nullptr;
   bool ok = false;
 };
-constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0;
+constexpr int kNcclUint32 = 3, kNcclUint64 = 5, kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0, kNcclMin = 3;   // nccl.h enums
 static NcclApi g_nccl;
 static int load_nccl() {
   if (g_nccl.ok) return 0;
@@ -186,6 +187,11 @@ struct dawn_unet {
 
   std::map<std::string, float*> taps;
   int64_t launches = 0;
+
+  // whole-clip sampling loop captured as one CUDA graph (dawn_unet_sampler_capture); invalidated by any geometry change
+  cudaGraphExec_t samp_exec = nullptr;
+  cudaStream_t samp_stream = nullptr;          // capture origin (the legacy default stream cannot be captured)
+  int64_t samp_launches = 0;
 
   // per-category kernel timing (CUDA events on the launching stream), see dawn_unet_profile_*
   bool prof_on = false;
@@ -1032,6 +1038,8 @@ int dawn_unet_create(const dawn_unet_cfg* cfg, dawn_unet** out) {
 void dawn_unet_destroy(dawn_unet* h) {
   if (!h) return;
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  if (h->samp_exec) cudaGraphExecDestroy(h->samp_exec);
+  if (h->samp_stream) cudaStreamDestroy(h->samp_stream);
   if (h->sh_comm && g_nccl.ok) g_nccl.CommDestroy(h->sh_comm);
   free_all(h->owned);
   free_all(h->ws_owned);
@@ -1048,8 +1056,13 @@ int dawn_unet_set_param(dawn_unet* h, const char* name, const float* host, const
   return 0;
 }
 
+static void drop_sampler_graph(dawn_unet* h) {
+  if (h->samp_exec) { cudaGraphExecDestroy(h->samp_exec); h->samp_exec = nullptr; }
+}
+
 int dawn_unet_commit_params(dawn_unet* h) {
   DAWN_CHECK(h, "null handle");
+  drop_sampler_graph(h);
   free_all(h->owned);
   h->rb.clear(); h->rb_index.clear();
   h->down_ta.clear(); h->up_ta.clear(); h->down_sla.clear(); h->up_sla.clear(); h->down_conv.clear(); h->up_conv.clear();
@@ -1120,6 +1133,7 @@ int dawn_unet_commit_params(dawn_unet* h) {
 
 int dawn_unet_set_num_frames(dawn_unet* h, int F, int height, int width) {
   DAWN_CHECK(h, "null handle");
+  drop_sampler_graph(h);
   DAWN_CHECK(h->committed, "commit_params must precede set_num_frames");
   DAWN_CHECK(F >= 1 && F <= 65535, "F out of range");
   const int nlev = h->nlev, dim = h->cfg.dim;
@@ -1347,6 +1361,7 @@ int dawn_unet_init_shard(dawn_unet* h, const char* id128, int nranks, int rank, 
   DAWN_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank");
   DAWN_CHECK(F_global == h->F * nranks, "F_global must equal nranks * local frames (equal contiguous frame ranges)");
   DAWN_CHECK(nranks == 1 || h->F >= h->cfg.win_width, "each rank must own at least win_width frames (only neighbours exchange halos)");
+  drop_sampler_graph(h);
   if (nranks > 1) {
     DAWN_TRY(load_nccl());
     if (h->sh_comm) { g_nccl.CommDestroy(h->sh_comm); h->sh_comm = nullptr; }
@@ -1361,6 +1376,73 @@ int dawn_unet_init_shard(dawn_unet* h, const char* id128, int nranks, int rank, 
   const int pos0 = rank * h->F - h->sh_halo_l;
   DAWN_TRY(launch_rotary_table(h->rot_freqs, h->sh_halo_l + h->F + h->sh_halo_r, pos0, h->ROT, 0));
   DAWN_CUDA_OK(cudaDeviceSynchronize());
+  return 0;
+}
+
+// DDIM update of this handle's frames (see sampler.cu).  Unsharded: identical to dawn_ddim_step.  Frame-sharded: the
+// clip-wide quantile (U:1186-1190) is selected over ALL ranks' values by all-reducing the radix-select's histograms
+// (4 x 256 u32) and its two tail statistics — 6 tiny collectives per step instead of gathering x0 (4.9 MB per rank).
+static int red_sum_u32(void* ctx, unsigned int* b, size_t n, cudaStream_t st) {
+  DAWN_NCCL_OK(g_nccl.AllReduce(b, b, n, kNcclUint32, kNcclSum, (ncclComm_t)ctx, st)); return 0;
+}
+static int red_sum_u64(void* ctx, unsigned long long* b, size_t n, cudaStream_t st) {
+  DAWN_NCCL_OK(g_nccl.AllReduce(b, b, n, kNcclUint64, kNcclSum, (ncclComm_t)ctx, st)); return 0;
+}
+static int red_min_u32(void* ctx, unsigned int* b, size_t n, cudaStream_t st) {
+  DAWN_NCCL_OK(g_nccl.AllReduce(b, b, n, kNcclUint32, kNcclMin, (ncclComm_t)ctx, st)); return 0;
+}
+int dawn_unet_ddim_step(dawn_unet* h, float* x, const float* eps, const float* noise, int64_t n_local, float ca, float cb,
+                        float sqrt_an, float c, float sigma, float q, void* scratch, void* stream) {
+  DAWN_CHECK(h, "null handle");
+  if (h->sh_nranks <= 1 || !h->sh_comm)
+    return ddim_step_impl(x, eps, noise, n_local, n_local, ca, cb, sqrt_an, c, sigma, q, scratch, (cudaStream_t)stream, nullptr);
+  DdimReduce red{(void*)h->sh_comm, red_sum_u32, red_sum_u64, red_min_u32};
+  return ddim_step_impl(x, eps, noise, n_local, n_local * h->sh_nranks, ca, cb, sqrt_an, c, sigma, q, scratch,
+                        (cudaStream_t)stream, &red);
+}
+
+// The whole sampling loop of one clip as ONE CUDA graph: nsteps x (forward_x3 + DDIM update), no host work
+// between steps.  Everything the graph touches is fixed at capture time: x (3,F,h,w) in/out, eps scratch, noise_all
+// ((nsteps-1) x n floats, step k reads slice k; the last step adds none, U:1201), t_all (nsteps int64 on the device), the
+// clip-invariant tables inside the handle (refresh them with set_clip_invariants before each launch: same addresses).
+// coef: host array nsteps x 5 = {ca, cb, sqrt_alpha_next, c, sigma} per step.
+int dawn_unet_sampler_capture(dawn_unet* h, float* x, float* eps, const float* noise_all, const int64_t* t_all,
+                              const float* coef, int nsteps, float q, void* scratch) {
+  DAWN_CHECK(h && x && eps && t_all && coef && scratch && nsteps >= 1, "bad argument");
+  DAWN_CHECK(noise_all || nsteps == 1, "noise_all is required for more than one step");
+  DAWN_CHECK(h->F > 0 && h->have_invariants, "set_clip_invariants must precede sampler_capture");
+  DAWN_CHECK(!h->prof_on, "disable profiling before capturing the sampler graph");
+  drop_sampler_graph(h);
+  if (!h->samp_stream) DAWN_CUDA_OK(cudaStreamCreateWithFlags(&h->samp_stream, cudaStreamNonBlocking));
+  const int64_t n = (int64_t)(h->cfg.out_grid_dim + h->cfg.out_conf_dim) * h->F * h->H * h->W;
+  cudaStream_t st = h->samp_stream;
+  DAWN_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int rc = 0;
+  int64_t launches = 0;
+  for (int k = 0; k < nsteps && rc == 0; ++k) {
+    rc = dawn_unet_forward_x3(h, x, t_all + k, eps, st);
+    launches += h->launches;
+    const float* cf = coef + 5 * k;
+    if (rc == 0)
+      rc = dawn_unet_ddim_step(h, x, eps, (k < nsteps - 1) ? noise_all + (size_t)k * n : nullptr, n, cf[0], cf[1], cf[2], cf[3], cf[4],
+                               q, scratch, st);
+  }
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(st, &graph);
+  if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+  DAWN_CUDA_OK(e);
+  const cudaError_t ei = cudaGraphInstantiate(&h->samp_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  DAWN_CUDA_OK(ei);
+  h->samp_launches = launches;
+  return 0;
+}
+
+int dawn_unet_sampler_launch(dawn_unet* h, void* stream) {
+  DAWN_CHECK(h && h->samp_exec, "sampler_capture must precede sampler_launch (a geometry change drops the graph)");
+  DAWN_CHECK(h->have_invariants, "set_clip_invariants must precede sampler_launch");
+  DAWN_CUDA_OK(cudaGraphLaunch(h->samp_exec, (cudaStream_t)stream));
+  h->launches = h->samp_launches;
   return 0;
 }
 

@@ -89,9 +89,17 @@ class GaussianDiffusion(nn.Module):
                                 cond_scale=cond_scale)
 
     @torch.no_grad()
-    def ddim_sample(self, fea, shape, cond=None, cond_scale=1., clip_denoised=True, noise_fn=None, pairs=None):
-        """fea (b, 272, h, w); cond (b, F, cond_dim).  noise_fn(step_index, shape) -> tensor lets tests inject the noise
-        the reference draws with torch.randn / randn_like (:1166, 1201)."""
+    def ddim_sample(self, fea, shape, cond=None, cond_scale=1., clip_denoised=True, noise_fn=None, pairs=None,
+                    use_graph=False, seed=None):
+        """fea (b, 272, h, w); cond (b, F, cond_dim); shape (b, 3, F, h, w).
+
+        noise_fn(step_index, shape) -> tensor lets tests inject the noise the reference draws with torch.randn /
+        randn_like (:1166, 1201); step_index -1 is the start image.
+        use_graph: replay the whole loop (nsteps x [UNet forward + DDIM update]) as ONE CUDA graph per clip
+        (`dawn_unet_sampler_capture`; captured once per geometry/schedule and cached on the module).
+        Frame-sharded UNet (`unet.init_shard`): `shape`, `cond` and the returned sample hold this rank's frames; the
+        dynamic-threshold quantile is selected over the whole clip (all-reduced radix select) and the default noise is
+        the rank's slice of ONE clip-wide stream (same `seed` on every rank; drawn on rank 0 and broadcast if None)."""
         if cond_scale != 1:
             raise NotImplementedError("cond_scale != 1 goes through DynamicNfUnet3D.forward_with_cond_scale (two forwards); "
                                       "the fused sampler implements DAWN's shipped cond_scale = 1.0")
@@ -99,13 +107,15 @@ class GaussianDiffusion(nn.Module):
         b, ch, Fr, h, w = shape
         unet = self.denoise_fn
         pairs = self.ddim_schedule() if pairs is None else pairs
-        draw = noise_fn if noise_fn is not None else (lambda k, shp: torch.randn(shp, device=device))
+        draw = noise_fn if noise_fn is not None else self._default_noise(unet, device, seed)
         img = draw(-1, shape).to(device).contiguous()
         n = ch * Fr * h * w
-        scratch = torch.empty(n + 512, dtype=torch.int32, device=device)
-        eps = torch.empty((ch, Fr, h, w), device=device)
         q = float(self.dynamic_thres_percentile) if (clip_denoised and self.use_dynamic_thres) else 0.0
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if use_graph:
+            return self._ddim_sample_graph(unet, fea, cond, img, pairs, draw, q, st)
+        scratch = torch.empty(n + 512, dtype=torch.int32, device=device)
+        eps = torch.empty((ch, Fr, h, w), device=device)
         for i in range(b):
             unet.update_num_frames(Fr)
             unet.set_clip_invariants(fea[i], cond[i])
@@ -115,10 +125,63 @@ class GaussianDiffusion(nn.Module):
                 unet.forward_x3(x, t_dev, eps)
                 ca, cb, san, c, sigma = self.ddim_coefficients(t, t_next)
                 noise = draw(k, (ch, Fr, h, w)).to(device).contiguous() if t_next > 0 else None
-                check(lib.dawn_ddim_step(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(eps.data_ptr()),
-                                         ctypes.c_void_p(noise.data_ptr()) if noise is not None else None, n,
-                                         ca, cb, san, c, sigma, q if clip_denoised else 0.0,
-                                         ctypes.c_void_p(scratch.data_ptr()), st), "dawn_ddim_step")
+                check(lib.dawn_unet_ddim_step(unet._handle, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(eps.data_ptr()),
+                                              ctypes.c_void_p(noise.data_ptr()) if noise is not None else None, n,
+                                              ca, cb, san, c, sigma, q,
+                                              ctypes.c_void_p(scratch.data_ptr()), st), "dawn_unet_ddim_step")
+        return img
+
+    @staticmethod
+    def _default_noise(unet, device, seed):
+        """torch.randn per step (:1166, 1201).  For a frame-sharded clip every rank draws the clip-wide tensor from the same
+        seeded generator and keeps its own frames, so the sample does not depend on the number of GPUs."""
+        rank, world = unet.shard_info() if hasattr(unet, "shard_info") else (0, 1)
+        if world == 1 and seed is None:
+            return lambda k, shp: torch.randn(shp, device=device)
+        if seed is None:
+            import torch.distributed as dist
+            box = [int(torch.randint(0, 2 ** 62, (1,)).item())]
+            dist.broadcast_object_list(box, src=0)
+            seed = box[0]
+        gen = torch.Generator(device=device)
+        gen.manual_seed(int(seed))
+
+        def draw(k, shp):
+            shp = tuple(shp)
+            Fl = shp[-3]
+            full = torch.randn(shp[:-3] + (Fl * world,) + shp[-2:], device=device, generator=gen)
+            return full[..., rank * Fl:(rank + 1) * Fl, :, :].contiguous()
+        return draw
+
+    def _ddim_sample_graph(self, unet, fea, cond, img, pairs, draw, q, st):
+        b, ch, Fr, h, w = img.shape
+        device, n, ns = img.device, ch * Fr * h * w, len(pairs)
+        key = (Fr, h, w, tuple(pairs), q, device.index)
+        g = getattr(self, "_graph", None)
+        unet.update_num_frames(Fr)
+        if g is None or g["key"] != key or g["gen"] != unet.graph_generation():
+            g = dict(key=key, x=torch.empty((ch, Fr, h, w), device=device), eps=torch.empty((ch, Fr, h, w), device=device),
+                     noise=torch.empty((max(ns - 1, 1), ch, Fr, h, w), device=device),
+                     t_all=torch.tensor([p[0] for p in pairs], dtype=torch.long, device=device),
+                     scratch=torch.empty(n + 512, dtype=torch.int32, device=device))
+            coef = (ctypes.c_float * (5 * ns))()
+            for k, (t, t_next) in enumerate(pairs):
+                coef[5 * k:5 * k + 5] = self.ddim_coefficients(t, t_next)
+                assert (t_next > 0) == (k < ns - 1), "only the last DDIM step ends at t = 0 (reference :1201)"
+            unet.set_clip_invariants(fea[0], cond[0])
+            torch.cuda.synchronize(device)
+            check(lib.dawn_unet_sampler_capture(unet._handle, ctypes.c_void_p(g["x"].data_ptr()), ctypes.c_void_p(g["eps"].data_ptr()),
+                                                ctypes.c_void_p(g["noise"].data_ptr()), ctypes.c_void_p(g["t_all"].data_ptr()),
+                                                coef, ns, q, ctypes.c_void_p(g["scratch"].data_ptr())), "dawn_unet_sampler_capture")
+            g["gen"] = unet.graph_generation()
+            self._graph = g
+        for i in range(b):
+            unet.set_clip_invariants(fea[i], cond[i])
+            g["x"].copy_(img[i])
+            for k in range(ns - 1):
+                g["noise"][k].copy_(draw(k, (ch, Fr, h, w)))
+            check(lib.dawn_unet_sampler_launch(unet._handle, st), "dawn_unet_sampler_launch")
+            img[i].copy_(g["x"])
         return img
 
     def forward(self, *a, **k):

@@ -258,6 +258,7 @@ class Unet3D(nn.Module):
             if self._geom != (F, h, w):
                 check(lib.dawn_unet_set_num_frames(self._handle, F, h, w), "dawn_unet_set_num_frames")
                 self._geom = (F, h, w)
+                self._gen = getattr(self, "_gen", 0) + 1
 
     def sync_parameters(self):
         """Repack the module's parameters into kernel layouts (once per parameter change)."""
@@ -272,6 +273,8 @@ class Unet3D(nn.Module):
         put("aux.rel_bias", _rel_bias_table(self.time_rel_pos_bias.relative_attention_bias.weight, self.win_width))
         check(lib.dawn_unet_commit_params(self._handle), "dawn_unet_commit_params")
         self._dirty = False
+        self._gen = getattr(self, "_gen", 0) + 1
+        self._shard = None          # commit re-runs set_num_frames in the library, which leaves the handle unsharded
         if self._geom is not None:
             self._geom = self._geom  # commit re-sized the per-clip tables for the current geometry
 
@@ -351,6 +354,19 @@ class Unet3D(nn.Module):
         dist.broadcast_object_list(box, src=0)
         with torch.cuda.device(device):
             check(lib.dawn_unet_init_shard(self._handle, box[0], world, rank, F_local * world), "dawn_unet_init_shard")
+        self._shard = (rank, world, (F_local, h, w))
+        self._gen = getattr(self, "_gen", 0) + 1
+
+    def shard_info(self):
+        """(rank, world) of the frame sharding in force for the current geometry; (0, 1) when unsharded."""
+        sh = getattr(self, "_shard", None)
+        if sh is None or sh[2] != self._geom:
+            return 0, 1
+        return sh[0], sh[1]
+
+    def graph_generation(self):
+        """Changes whenever the native handle dropped a captured sampler graph (new geometry, parameters or sharding)."""
+        return (id(self._handle), getattr(self, "_gen", 0))
 
     def forward_x3(self, x_t, time, out=None):
         """x_t (3, F, h, w) of the clip whose invariants were set; time int64 tensor (1,) on the device."""

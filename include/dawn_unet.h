@@ -110,6 +110,24 @@ int64_t dawn_unet_workspace_bytes(dawn_unet* h);
 int dawn_ddim_step(float* x, const float* eps, const float* noise, int64_t n, float ca, float cb, float sqrt_an, float c,
                    float sigma, float q, void* scratch, void* stream);
 
+/* The same update for the frames a handle owns.  Unsharded handle: identical to dawn_ddim_step.  After dawn_unet_init_shard
+ * the quantile spans the whole clip (n_local * nranks values): the radix-select's four 256-bin histograms and its two tail
+ * statistics are all-reduced (NCCL, on `stream`), so every rank applies the bit-identical threshold.  Every rank must call
+ * it with the same coefficients; `noise` is this rank's slice of the clip's noise. */
+int dawn_unet_ddim_step(dawn_unet* h, float* x, const float* eps, const float* noise, int64_t n_local, float ca, float cb,
+                        float sqrt_an, float c, float sigma, float q, void* scratch, void* stream);
+
+/* The whole sampling loop of one clip (reference ddim_sample :1156-1208: 20 x [UNet forward + DDIM update]) captured
+ * once into ONE CUDA graph and replayed per clip with a single launch: no host work between steps.  All addresses are
+ * fixed at capture: x (3,F,h,w) start noise in / sample out, eps (3,F,h,w) scratch, noise_all ((nsteps-1) x 3*F*h*w,
+ * slice k feeds step k; the last step adds none), t_all (nsteps int64, device), scratch (as dawn_ddim_step).
+ * coef (host): nsteps x {ca, cb, sqrt_alpha_next, c, sigma}.  Per clip: fill x / noise_all, call
+ * dawn_unet_set_clip_invariants (rewrites the same tables), then dawn_unet_sampler_launch(stream).
+ * set_num_frames / commit_params / init_shard drop the graph. */
+int dawn_unet_sampler_capture(dawn_unet* h, float* x, float* eps, const float* noise_all, const int64_t* t_all,
+                              const float* coef, int nsteps, float q, void* scratch);
+int dawn_unet_sampler_launch(dawn_unet* h, void* stream);
+
 /* self-test of the tcgen05 contraction kernel against the mma.sync kernel on a random k x k convolution
  * (F frames of H x W, Cin -> N channels); reports max |difference| (outputs and, if requested, GroupNorm sums). */
 int dawn_selftest_tc_gemm(int F, int H, int W, int Cin, int N, int ksize, int with_stats, float* max_abs_diff, float* max_abs_ref);

@@ -102,3 +102,43 @@ def sharded_unet_forward(sd, cfg, x_local, time, cond_local, F_global):
             O.rel_pos_bias = orig_bias
     finally:
         O.clip_groupnorm, O.temporal_attention = orig_gn, orig_ta
+
+
+def sharded_dynamic_threshold(x0_local, q):
+    """TEST INFRASTRUCTURE — host-side logic of `dawn_unet_ddim_step` on a frame-sharded clip (csrc/sampler.cu,
+    SURVEY 8e-iii): s = max(1, torch.quantile(|x0|.flatten(), q)) over the WHOLE clip (reference U:1186-1193) without
+    gathering x0.  Non-negative fp32 values order like their bit patterns, so the order statistic `lo = floor(q*(n-1))` is
+    found by a 4-pass radix select over 8-bit digits whose 256-bin histograms are all-reduced; one more pass gives the
+    count of keys <= v[lo] and the smallest key above it (all-reduced sum / min), enough for torch's linear interpolation."""
+    import numpy as np
+    keys = x0_local.detach().abs().float().contiguous().view(-1).numpy().view(np.uint32)
+    n_local = keys.size
+    n_global = n_local * dist.get_world_size()
+    rank_f = np.float32(q) * np.float32(n_global - 1)                 # ATen evaluates the rank in the input dtype
+    lo, hi = int(np.floor(rank_f)), int(np.ceil(rank_f))
+    w = np.float32(rank_f - np.floor(rank_f))
+    prefix, mask, rem = np.uint32(0), np.uint32(0), lo
+    for shift in (24, 16, 8, 0):
+        sel = keys[(keys & mask) == prefix]
+        hist = torch.from_numpy(np.bincount((sel >> np.uint32(shift)) & np.uint32(255), minlength=256).astype(np.int64))
+        dist.all_reduce(hist)
+        cum = 0
+        for b in range(256):
+            if cum + int(hist[b]) > rem:
+                break
+            cum += int(hist[b])
+        rem -= cum
+        prefix = np.uint32(prefix | np.uint32(b << shift))
+        mask = np.uint32(mask | np.uint32(255 << shift))
+    count_le = torch.tensor([int((keys <= prefix).sum())], dtype=torch.int64)
+    above = keys[keys > prefix]
+    min_gt = torch.tensor([int(above.min()) if above.size else 0xFFFFFFFF], dtype=torch.int64)
+    dist.all_reduce(count_le)
+    dist.all_reduce(min_gt, op=dist.ReduceOp.MIN)
+    vlo = np.array([prefix], dtype=np.uint32).view(np.float32)[0]
+    vhi = vlo
+    if hi > lo and int(count_le) < lo + 2:
+        vhi = np.array([int(min_gt)], dtype=np.uint32).view(np.float32)[0]
+    d = np.float32(vhi - vlo)
+    qv = np.float32(vlo + w * d) if w < 0.5 else np.float32(vhi - d * (np.float32(1) - w))      # at::lerp
+    return float(max(qv, np.float32(1.0))), float(qv)

@@ -80,3 +80,40 @@ def test_partition_plan_arithmetic():
             assert max(0, lo - win) >= pos0 and min(world * Fl, hi + win) <= hi + hr
             covered += list(range(lo, hi))
         assert covered == list(range(world * Fl))
+
+
+def _quantile_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import sharded as S
+        res = []
+        for seed, n_local, scale, qq in ((0, 3 * 48 * 8 * 8, 1.7, 0.9), (1, 1000, 0.2, 0.9), (2, 7, 3.0, 0.5), (3, 4096, 1.0, 0.999)):
+            g = torch.Generator().manual_seed(seed)
+            full = torch.randn(world * n_local, generator=g) * scale
+            if seed == 2:
+                full[:] = full[0]                          # all keys equal: ties on every digit
+            s, qv = S.sharded_dynamic_threshold(full[rank * n_local:(rank + 1) * n_local], qq)
+            ref = torch.quantile(full.abs(), qq)
+            res.append((s, qv, float(ref), float(ref.clamp(min=1.0))))
+        if rank == 0:
+            q.put(res)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_dynamic_threshold_equals_torch_quantile_world2():
+    """Row a16 under sharding: the all-reduced radix select gives torch.quantile's value bit for bit."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_quantile_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for s, qv, ref, ref_s in q.get(timeout=5):
+        assert qv == ref, (qv, ref)
+        assert s == ref_s

@@ -166,3 +166,76 @@ def test_ddim_sampler_steps_match_reference_golden():
         d = (img.cpu() - ref).abs().max().item()
         print(f"ddim {nsteps} step(s): max|d| = {d:.3e}")
         assert d < 2e-4
+
+
+def _odd_sampler():
+    from dawn_pytorch_b200 import DynamicNfGaussianDiffusion
+    net = G.cuda_net()
+    D = DynamicNfGaussianDiffusion(denoise_fn=net, num_frames=40, image_size=32, sampling_timesteps=20, timesteps=1000,
+                                   loss_type='l2', use_dynamic_thres=True, null_cond_prob=0.1, ddim_sampling_eta=1.0).cuda()
+    F, h, w, _ = G.CASES["odd"]
+    x_t, fea, cond = W.synth_inputs("odd", F, h, w)
+    D.update_num_frames(F)
+
+    def noise_fn(k, shape):
+        if k < 0:
+            return x_t.clone()
+        return torch.from_numpy(W.pseudo_normal(f"odd/noise{k}", (1,) + tuple(shape)))[0]
+    return D, (F, h, w), fea, cond, noise_fn
+
+
+def test_graph_captured_sampler_matches_golden_and_eager():
+    """Row N2: the whole DDIM loop as ONE CUDA graph (dawn_unet_sampler_capture/launch) == the eager loop == the
+    reference's arithmetic (golden, injected noise); a second clip replays the cached graph."""
+    D, (F, h, w), fea, cond, noise_fn = _odd_sampler()
+    g = np.load(__import__("os").path.join(G.ROOT, "tests", "golden", "ddim_odd.npz"))
+    steps = [tuple(int(v) for v in p) for p in g["steps"].tolist()]
+    eager = D.ddim_sample(fea.cuda(), (1, 3, F, h, w), cond=cond.cuda(), noise_fn=noise_fn, pairs=steps).clone()
+    graph = D.ddim_sample(fea.cuda(), (1, 3, F, h, w), cond=cond.cuda(), noise_fn=noise_fn, pairs=steps, use_graph=True).clone()
+    torch.cuda.synchronize()
+    n_launch = D.denoise_fn.last_launch_count()
+    ref = torch.from_numpy(g["x_after"][len(steps) - 1])
+    print(f"graph sampler: vs golden {(graph.cpu() - ref).abs().max():.3e}, vs eager {(graph - eager).abs().max():.3e}, "
+          f"{n_launch} kernel launches in one graph")
+    assert (graph.cpu() - ref).abs().max().item() < 2e-4
+    assert (graph - eager).abs().max().item() < 5e-5
+    assert n_launch >= 3 * 200
+    # replay on a second clip (other conditioning): the cached graph must pick up the refreshed clip invariants
+    gen0 = D._graph["gen"]
+    cond2 = cond.flip(1).contiguous()
+    e2 = D.ddim_sample(fea.cuda(), (1, 3, F, h, w), cond=cond2.cuda(), noise_fn=noise_fn, pairs=steps).clone()
+    g2 = D.ddim_sample(fea.cuda(), (1, 3, F, h, w), cond=cond2.cuda(), noise_fn=noise_fn, pairs=steps, use_graph=True).clone()
+    torch.cuda.synchronize()
+    assert D._graph["gen"] == gen0                       # no re-capture
+    assert (g2 - e2).abs().max().item() < 5e-5
+    assert (g2 - graph).abs().max().item() > 1e-3        # and it really is a different clip
+
+
+def test_handle_ddim_step_equals_plain_entry_unsharded():
+    """dawn_unet_ddim_step on an unsharded handle is dawn_ddim_step (same kernels, n_global = n)."""
+    import ctypes
+    from dawn_pytorch_b200._lib import lib, check
+    net = G.cuda_net()
+    net.update_num_frames(8)
+    x, t, cond, x_t, fea = G.clip("smoke", 8, 8, 8, 500)
+    net.set_clip_invariants(fea[0].cuda(), cond[0].cuda())          # makes sure the handle exists
+    gen = torch.Generator().manual_seed(5)
+    n = 3 * 37 * 16 * 16
+    xa = (torch.randn(n, generator=gen) * 1.5).cuda()
+    eps, noise = torch.randn(n, generator=gen).cuda(), torch.randn(n, generator=gen).cuda()
+    xb = xa.clone()
+    scratch = torch.empty(n + 512, dtype=torch.int32, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    args = (n, 1.3, 0.8, 0.9, 0.3, 0.2, 0.9, ctypes.c_void_p(scratch.data_ptr()), st)
+    check(lib.dawn_ddim_step(ctypes.c_void_p(xa.data_ptr()), ctypes.c_void_p(eps.data_ptr()), ctypes.c_void_p(noise.data_ptr()), *args), "a")
+    check(lib.dawn_unet_ddim_step(net._handle, ctypes.c_void_p(xb.data_ptr()), ctypes.c_void_p(eps.data_ptr()),
+                                  ctypes.c_void_p(noise.data_ptr()), *args), "b")
+    torch.cuda.synchronize()
+    assert torch.equal(xa, xb)
+    # against torch's own quantile arithmetic (reference U:1183-1205)
+    xr = (torch.randn(n, generator=torch.Generator().manual_seed(5)) * 1.5)
+    e, nz = eps.cpu(), noise.cpu()
+    x0 = 1.3 * xr - 0.8 * e
+    s = torch.quantile(x0.abs(), 0.9).clamp(min=1.0)
+    ref = x0.clamp(-s, s) / s * 0.9 + 0.3 * e + 0.2 * nz
+    assert (xa.cpu() - ref).abs().max().item() < 2e-6

@@ -19,4 +19,4 @@ out = torch.empty((3, bench.F_CLIP, bench.H_LAT, bench.W_LAT), device="cuda")
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
     net.forward_x3(x_t.cuda(), t, out)
 torch.cuda.synchronize()
-print("done", float(out.abs().max()))
+print("done", float(out.abs().max()), "launches/step", net.last_launch_count())

@@ -12,6 +12,50 @@ from oracle import weights as W            # noqa: E402
 from tests import gpu_common as G          # noqa: E402
 
 
+def sampler_case(net, rank, world, dev):
+    """Row a16 under sharding: 3 DDIM steps (first, middle, last of the 20-step schedule) on a frame-sharded clip — clip-wide
+    quantile through all-reduced radix select, per-rank slice of one clip-wide noise tensor — vs the single-GPU sampler."""
+    from dawn_pytorch_b200 import DynamicNfGaussianDiffusion, DynamicNfUnet3D
+    Fg, h, w = 48 * world, 16, 16
+    Fl, lo = Fg // world, rank * (Fg // world)
+    x_t, fea, cond = W.synth_inputs("shardddim", Fg, h, w)
+
+    def make(unet):
+        return DynamicNfGaussianDiffusion(denoise_fn=unet, num_frames=40, image_size=32, sampling_timesteps=20, timesteps=1000,
+                                          loss_type='l2', use_dynamic_thres=True, null_cond_prob=0.1, ddim_sampling_eta=1.0).to(dev)
+    D = make(net)
+    sched = D.ddim_schedule()
+    pairs = [sched[0], sched[10], sched[-1]]
+
+    def noise_global(k):
+        return x_t[0] if k < 0 else torch.from_numpy(W.pseudo_normal(f"shardddim/noise{k}", (3, Fg, h, w)))
+
+    net.update_num_frames(Fl)
+    net.init_shard(Fl, h, w, dev)
+    assert net.shard_info() == (rank, world)
+    D.update_num_frames(Fl)
+    for use_graph in (False, True):
+        out = D.ddim_sample(fea.to(dev), (1, 3, Fl, h, w), cond=cond[:, lo:lo + Fl].contiguous().to(dev), pairs=pairs,
+                            noise_fn=lambda k, shp: noise_global(k)[:, lo:lo + Fl].reshape(shp).clone(), use_graph=use_graph)[0].clone()
+        parts = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(parts, out)
+        full = torch.cat(parts, dim=1).cpu()
+        if rank == 0:
+            net1 = DynamicNfUnet3D(**G.CTOR).eval()
+            net1.load_state_dict(G.synth_sd(), strict=True)
+            D1 = make(net1.to(dev))
+            D1.update_num_frames(Fg)
+            one = D1.ddim_sample(fea.to(dev), (1, 3, Fg, h, w), cond=cond.to(dev), pairs=pairs,
+                                 noise_fn=lambda k, shp: noise_global(k).reshape(shp).clone())[0].cpu()
+            print(f"[ddim] F={Fg} sharded x{world} sampler ({'graph' if use_graph else 'eager'}), 3 steps: max|d| vs single-GPU {(full - one).abs().max():.2e}",
+                  flush=True)
+            del D1, net1
+        dist.barrier()
+    # default noise: one clip-wide stream, sliced per rank
+    a = D.ddim_sample(fea.to(dev), (1, 3, Fl, h, w), cond=cond[:, lo:lo + Fl].contiguous().to(dev), pairs=pairs[:2], seed=123)
+    assert torch.isfinite(a).all()
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
@@ -57,6 +101,7 @@ def main():
                   f"  max|d| {(full[0] - one.cpu()).abs().max():.2e};  sharded step {ms:.2f} ms", flush=True)
             del net1
         dist.barrier()
+    sampler_case(net, rank, world, dev)
     dist.destroy_process_group()
 
 
