@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_kernel(const GemmParams p) {
   __shared__ float s_stat[16];
   __shared__ float s_gn[16];
 
+  if (p.skip_flag && *p.skip_flag == p.skip_if) return;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int wm = warp & 3, wn = warp >> 2;

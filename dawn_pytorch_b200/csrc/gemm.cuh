@@ -59,6 +59,7 @@ struct GemmParams {
   const float* Y; int ldy; const double* gn_stats; const float* gn_w; const float* gn_b;
   const float* film;       // [2N] scale | shift, or null
   double gn_count;         // elements per group
+  const int* skip_flag; int skip_if;   // mma.sync kernel only: return at once when *skip_flag == skip_if (device-side path selection)
   int exp_shift;               // experiment (tcgen05 path, BN = 64): A operand stored/addressed this many rows into the swizzle atom
   unsigned long long* trace;   // optional [16] cycle counters written by CTA 0 of the tcgen05 kernel (debug)
 };

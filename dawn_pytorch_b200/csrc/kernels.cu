@@ -143,6 +143,61 @@ __global__ void cond_kv_batched_kernel(const CondDesc* __restrict__ descs) {
   frame_linear_body<0>(d.ctx, d.n1, 0, d.n1, d.Wkv, nullptr, 128, d.kv);
 }
 
+// v2 of the batched per-clip conditioning layers: a block owns FL_JT*8 = 32 outputs x FL_FT = 8 frames, so every weight row
+// is read once per 8 frames (v1: once per frame — 200 x 35 MB through L2 for the audio MLPs) and SiLU(cond) is evaluated
+// once per 32 outputs (v1: per 8).  Each (frame, output) keeps v1's arithmetic order exactly (lane-strided partial sums,
+// butterfly reduction), so the tables are bit-identical.
+constexpr int FL_FT = 8, FL_JT = 4;
+template <int ACT>
+__device__ __forceinline__ void frame_linear_tiled_body(const float* __restrict__ x, int ldx, int off, int K,
+                                                        const float* __restrict__ W, const float* __restrict__ b, int Nout,
+                                                        float* __restrict__ out, int F) {
+  extern __shared__ float sx[];                 // [FL_FT][K]
+  const int f0 = blockIdx.y * FL_FT;
+  for (int i = threadIdx.x; i < FL_FT * K; i += blockDim.x) {
+    const int ft = i / K, k = i - ft * K;
+    float v = 0.f;
+    if (f0 + ft < F) { v = x[(size_t)(f0 + ft) * ldx + off + k]; v = ACT ? silu(v) : v; }
+    sx[i] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j0 = (blockIdx.x * (blockDim.x >> 5) + warp) * FL_JT;
+  if (j0 >= Nout) return;
+  float acc[FL_JT][FL_FT];
+#pragma unroll
+  for (int jj = 0; jj < FL_JT; ++jj)
+#pragma unroll
+    for (int ft = 0; ft < FL_FT; ++ft) acc[jj][ft] = 0.f;
+  for (int i = lane; i < K; i += 32) {
+    float wv[FL_JT];
+#pragma unroll
+    for (int jj = 0; jj < FL_JT; ++jj) wv[jj] = (j0 + jj < Nout) ? W[(size_t)(j0 + jj) * K + i] : 0.f;
+#pragma unroll
+    for (int ft = 0; ft < FL_FT; ++ft) {
+      const float xv = sx[ft * K + i];
+#pragma unroll
+      for (int jj = 0; jj < FL_JT; ++jj) acc[jj][ft] += wv[jj] * xv;
+    }
+  }
+#pragma unroll
+  for (int jj = 0; jj < FL_JT; ++jj)
+#pragma unroll
+    for (int ft = 0; ft < FL_FT; ++ft) {
+      const float r = warp_sum(acc[jj][ft]);
+      if (lane == 0 && j0 + jj < Nout && f0 + ft < F) out[(size_t)(f0 + ft) * Nout + j0 + jj] = r + (b ? b[j0 + jj] : 0.f);
+    }
+}
+__global__ void __launch_bounds__(256) cond_mlp_tiled_kernel(const float* __restrict__ cond, int cond_ld, const CondDesc* __restrict__ descs, int F) {
+  const CondDesc d = descs[blockIdx.z];
+  if ((int)blockIdx.x * 8 * FL_JT >= d.n1) return;
+  frame_linear_tiled_body<1>(cond, cond_ld, d.off, d.K, d.mW, d.mB, d.n1, d.ctx, F);
+}
+__global__ void __launch_bounds__(256) cond_kv_tiled_kernel(const CondDesc* __restrict__ descs, int F) {
+  const CondDesc d = descs[blockIdx.z];
+  frame_linear_tiled_body<0>(d.ctx, d.n1, 0, d.n1, d.Wkv, nullptr, 128, d.kv, F);
+}
+
 int launch_cond_mlp(const float* cond, int cond_ld, int off, int K, const float* W, const float* b, int Nout,
                     int F, float* out, cudaStream_t st) {
   dim3 grid((Nout + 7) / 8, F);
@@ -162,6 +217,7 @@ int launch_linear_nobias(const float* x, int K, const float* W, int Nout, int F,
 //   o_h = nv + w_h (v_h - nv),  so  to_out(o) = u_0 + sum_h w_h u_h  with per-frame vectors
 //   u_0 = Wout * rep(nv),  u_h = Wout[:, h] (v_h - nv)   (U:530-559).
 // The output LayerNorm (U:511-514) of that combination needs only the centred vectors and their Gram matrix.
+template <bool V2>
 __device__ __forceinline__ void ca_tables_body(const CaTableArgs& a, int f) {
   extern __shared__ float sm[];
   float* u = sm;                       // [9][co]
@@ -187,7 +243,29 @@ __device__ __forceinline__ void ca_tables_body(const CaTableArgs& a, int f) {
     const float inv = 1.0f / fmaxf(sqrtf(n2), 1e-12f);
     a.nkq[a.ca * 8 + tid] = s_nk[tid] * inv * a.ks[tid] * a.qs[tid];
   }
-  // u vectors
+  // u vectors.  V2: a thread owns output channel c, reads its 64-float Wout row once (16 x LDG.128) and forms all nine
+  // combinations from registers — v1 re-read the row for each of the 9 vectors with a 256-byte lane stride.  Same sums, same order.
+  if (V2) {
+    for (int c = tid; c < co; c += blockDim.x) {
+      float w[64];
+      const float4* wr = reinterpret_cast<const float4*>(a.Wout + (size_t)c * 64);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { const float4 t = __ldg(wr + i); w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w; }
+      float acc0 = 0.f;
+#pragma unroll
+      for (int h = 0; h < 8; ++h)
+#pragma unroll
+        for (int d = 0; d < 8; ++d) acc0 += w[h * 8 + d] * s_nv[d];
+      u[c] = acc0;
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        float acc = 0.f;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) acc += w[h * 8 + d] * (s_kv[64 + h * 8 + d] - s_nv[d]);
+        u[(h + 1) * co + c] = acc;
+      }
+    }
+  } else
   for (int idx = tid; idx < 9 * co; idx += blockDim.x) {
     const int r = idx / co, c = idx - r * co;
     const float* w = a.Wout + (size_t)c * 64;
@@ -229,13 +307,33 @@ __device__ __forceinline__ void ca_tables_body(const CaTableArgs& a, int f) {
   }
 }
 
-__global__ void ca_tables_kernel(CaTableArgs a) { ca_tables_body(a, blockIdx.x); }
-__global__ void ca_tables_batched_kernel(const CondDesc* __restrict__ descs) { ca_tables_body(descs[blockIdx.y].t, blockIdx.x); }
+__global__ void ca_tables_kernel(CaTableArgs a) { ca_tables_body<false>(a, blockIdx.x); }
+__global__ void ca_tables_batched_kernel(const CondDesc* __restrict__ descs) { ca_tables_body<false>(descs[blockIdx.y].t, blockIdx.x); }
+__global__ void __launch_bounds__(256) ca_tables_batched_v2_kernel(const CondDesc* __restrict__ descs) { ca_tables_body<true>(descs[blockIdx.y].t, blockIdx.x); }
 
 int launch_cond_batched(const float* cond, int cond_ld, const CondDesc* descs_dev, int ndesc, int max_n1, int max_k, int max_co, int F,
                         cudaStream_t st) {
   static size_t attr = 0;
+  static const bool v1 = [] { const char* e = getenv("DAWN_PREP_V1"); return e && e[0] == '1'; }();
   const size_t smem_kv = (size_t)max_n1 * sizeof(float), smem_t = (size_t)9 * max_co * sizeof(float);
+  if (!v1) {
+    const size_t sm1 = (size_t)FL_FT * max_k * sizeof(float), sm2 = (size_t)FL_FT * max_n1 * sizeof(float);
+    static size_t attr2 = 0;
+    if (std::max({sm1, sm2, smem_t}) > 48 * 1024 && std::max({sm1, sm2, smem_t}) > attr2) {
+      attr2 = std::max({sm1, sm2, smem_t});
+      DAWN_CUDA_OK(cudaFuncSetAttribute(cond_mlp_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attr2));
+      DAWN_CUDA_OK(cudaFuncSetAttribute(cond_kv_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attr2));
+      DAWN_CUDA_OK(cudaFuncSetAttribute(ca_tables_batched_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attr2));
+    }
+    const int ft = (F + FL_FT - 1) / FL_FT, jb = 8 * FL_JT;
+    cond_mlp_tiled_kernel<<<dim3((max_n1 + jb - 1) / jb, ft, ndesc), 256, sm1, st>>>(cond, cond_ld, descs_dev, F);
+    DAWN_LAUNCH_OK();
+    cond_kv_tiled_kernel<<<dim3((128 + jb - 1) / jb, ft, ndesc), 256, sm2, st>>>(descs_dev, F);
+    DAWN_LAUNCH_OK();
+    ca_tables_batched_v2_kernel<<<dim3(F, ndesc), 256, smem_t, st>>>(descs_dev);
+    DAWN_LAUNCH_OK();
+    return 0;
+  }
   if (smem_kv > 48 * 1024 || smem_t > 48 * 1024) {
     if (std::max(smem_kv, smem_t) > attr) {
       DAWN_CUDA_OK(cudaFuncSetAttribute(cond_kv_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem_kv, smem_t)));
@@ -614,8 +712,9 @@ int launch_sla_context(const float* qkv, int ld, int F, int P, const float* Wout
 // =========================================================================== layout transforms / init conv / heads
 // x[c][f][p] -> out[f][p][c_dst0 + c] (Cpad channels per pixel).  Channels outside [c_dst0, c_dst0+C) are zeroed.
 __global__ void ncf_to_nhwc_kernel(const float* __restrict__ x, int C, int F, int HW, int Cpad, int c_dst0,
-                                   float* __restrict__ out) {
+                                   float* __restrict__ out, const int* __restrict__ skip_flag, int skip_if) {
   __shared__ float tile[32][33];
+  if (skip_flag && *skip_flag == skip_if) return;
   const int f = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;       // c0 indexes destination channels
   const int tx = threadIdx.x, ty = threadIdx.y;               // (32, 8)
@@ -631,18 +730,91 @@ __global__ void ncf_to_nhwc_kernel(const float* __restrict__ x, int C, int F, in
     if (p < HW && cd < Cpad) out[((size_t)f * HW + p) * Cpad + cd] = tile[tx][k];
   }
 }
-int launch_ncf_to_nhwc(const float* x, int C, int F, int HW, int Cpad, int c_dst0, float* out, cudaStream_t st) {
+int launch_ncf_to_nhwc(const float* x, int C, int F, int HW, int Cpad, int c_dst0, float* out, cudaStream_t st,
+                       const int* skip_flag, int skip_if) {
   dim3 grid((HW + 31) / 32, (Cpad + 31) / 32, F);
-  ncf_to_nhwc_kernel<<<grid, dim3(32, 8), 0, st>>>(x, C, F, HW, Cpad, c_dst0, out);
+  ncf_to_nhwc_kernel<<<grid, dim3(32, 8), 0, st>>>(x, C, F, HW, Cpad, c_dst0, out, skip_flag, skip_if);
   DAWN_LAUNCH_OK();
+  return 0;
+}
+
+// Per-clip constant part of the k x k init conv as k row-convolutions that run side by side: copy s of the feature frame is
+// the frame shifted by (s - pad) rows (zero outside), so row ky of the kernel becomes a 1 x k conv over copy ky and the k
+// partial maps only need adding.  One frame of 64x64 pixels is 32 row tiles of the contraction kernel: k copies = k x 32 CTAs.
+// x[c][p] -> out[s][p][c_dst0 + c], Cpad channels per pixel, other channels zero.
+__global__ void fea_shift_nhwc_kernel(const float* __restrict__ x, long long cstride, int C, int H, int W, int Cpad, int c_dst0, int pad,
+                                      float* __restrict__ out, const int* __restrict__ skip_flag, int skip_if) {
+  __shared__ float tile[32][33];
+  if (skip_flag && *skip_flag == skip_if) return;
+  const int s = blockIdx.z, HW = H * W, shift = (s - pad) * W;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;               // (32, 8)
+  for (int k = ty; k < 32; k += 8) {
+    const int cd = c0 + k, cs = cd - c_dst0, p = p0 + tx, ps = p + shift;
+    float v = 0.f;
+    if (cs >= 0 && cs < C && p < HW && ps >= 0 && ps < HW) v = x[(size_t)cs * cstride + ps];
+    tile[k][tx] = v;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int p = p0 + k, cd = c0 + tx;
+    if (p < HW && cd < Cpad) out[((size_t)s * HW + p) * Cpad + cd] = tile[tx][k];
+  }
+}
+int launch_fea_shift_nhwc(const float* x, long long cstride, int C, int H, int W, int Cpad, int c_dst0, int k, float* out, cudaStream_t st,
+                          const int* skip_flag, int skip_if) {
+  dim3 grid((H * W + 31) / 32, (Cpad + 31) / 32, k);
+  fea_shift_nhwc_kernel<<<grid, dim3(32, 8), 0, st>>>(x, cstride, C, H, W, Cpad, c_dst0, k / 2, out, skip_flag, skip_if);
+  DAWN_LAUNCH_OK();
+  return 0;
+}
+// map[i] = bias[i % Co] + sum_s part[s][i]   (fixed order: deterministic)
+__global__ void map_reduce_kernel(const float* __restrict__ part, int nsplit, long long n, const float* __restrict__ bias, int Co,
+                                  float* __restrict__ map, const int* __restrict__ skip_flag, int skip_if) {
+  if (skip_flag && *skip_flag == skip_if) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = bias ? bias[(int)(i % Co)] : 0.f;
+  for (int s = 0; s < nsplit; ++s) acc += part[(size_t)s * n + i];
+  map[i] = acc;
+}
+int launch_map_reduce(const float* part, int nsplit, long long n, const float* bias, int Co, float* map, cudaStream_t st,
+                      const int* skip_flag, int skip_if) {
+  map_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(part, nsplit, n, bias, Co, map, skip_flag, skip_if);
+  DAWN_LAUNCH_OK();
+  return 0;
+}
+
+// flag = 1 iff some channel c in [c0, C) of x (C, F, HW) differs between frame 0 and any other frame (bit compare: NaNs and
+// signed zeros count as different -> the general path).  The reference's sampler tiles the per-clip features over the frames
+// (U:1167 `fea.repeat`), so the general entry can take the hoisted init conv whenever this finds no difference.
+__global__ void frame_invariance_kernel(const float* __restrict__ x, int c0, int C, int F, int HW, int* __restrict__ flag) {
+  const long long per_c = (long long)(F - 1) * HW, total = (long long)(C - c0) * per_c;
+  bool diff = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = c0 + (int)(i / per_c);
+    const long long r = i - (long long)(c - c0) * per_c;
+    const int p = (int)(r % HW);
+    const float* base = x + (size_t)c * F * HW;
+    diff |= __float_as_uint(base[HW + r]) != __float_as_uint(base[p]);
+  }
+  if (__any_sync(0xffffffffu, diff) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+int launch_frame_invariance(const float* x, int c0, int C, int F, int HW, int* flag, cudaStream_t st) {
+  DAWN_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  if (F > 1 && C > c0) {
+    frame_invariance_kernel<<<148 * 8, 256, 0, st>>>(x, c0, C, F, HW, flag);
+    DAWN_LAUNCH_OK();
+  }
   return 0;
 }
 
 // hoisted init conv: only the 3 noisy channels change per step; the 272 feature channels are a per-clip map
 __global__ void init_conv_x3_kernel(const float* __restrict__ xt, int F, int H, int W,
                                     const float* __restrict__ w3, const float* __restrict__ map, int Co,
-                                    float* __restrict__ out, int ldo, int ksz) {
+                                    float* __restrict__ out, int ldo, int ksz, const int* __restrict__ skip_flag, int skip_if) {
   extern __shared__ float sw[];                 // [ksz*ksz*3][Co]
+  if (skip_flag && *skip_flag == skip_if) return;
   const int ntap = ksz * ksz * 3;
   for (int i = threadIdx.x; i < ntap * Co; i += blockDim.x) sw[i] = w3[i];
   __syncthreads();
@@ -680,9 +852,11 @@ __global__ void init_conv_x3_kernel(const float* __restrict__ xt, int F, int H, 
 template <int KS>
 __global__ void __launch_bounds__(128) init_conv_x3_tiled_kernel(const float* __restrict__ xt, int F, int H, int W,
                                                                  const float* __restrict__ w3, const float* __restrict__ map,
-                                                                 float* __restrict__ out, int ldo) {
+                                                                 float* __restrict__ out, int ldo, const int* __restrict__ skip_flag,
+                                                                 int skip_if) {
   constexpr int PAD = KS / 2, TW = 64, TR = 8, IR = TR + KS - 1, ILD = 72, NW = KS * KS * 3 * 64;
   extern __shared__ __align__(16) float sm_ic[];
+  if (skip_flag && *skip_flag == skip_if) return;
   float* sw = sm_ic;                            // [KS*KS*3][64]
   float* sx = sm_ic + NW;                       // [3][IR][ILD]
   const int tid = threadIdx.x;
@@ -748,7 +922,7 @@ __global__ void __launch_bounds__(128) init_conv_x3_tiled_kernel(const float* __
 }
 
 int launch_init_conv_x3(const float* xt, int F, int H, int W, const float* w3, const float* map, int Co,
-                        float* out, int ldo, int ksz, cudaStream_t st) {
+                        float* out, int ldo, int ksz, cudaStream_t st, const int* skip_flag, int skip_if) {
   if (ksz == 7 && Co == 64) {
     constexpr size_t smem_t = (size_t)(7 * 7 * 3 * 64 + 3 * (8 + 6) * 72) * sizeof(float);
     static bool attr_t = false;
@@ -756,7 +930,7 @@ int launch_init_conv_x3(const float* xt, int F, int H, int W, const float* w3, c
       DAWN_CUDA_OK(cudaFuncSetAttribute(init_conv_x3_tiled_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
       attr_t = true;
     }
-    init_conv_x3_tiled_kernel<7><<<dim3((W + 63) / 64, (H + 7) / 8, F), 128, smem_t, st>>>(xt, F, H, W, w3, map, out, ldo);
+    init_conv_x3_tiled_kernel<7><<<dim3((W + 63) / 64, (H + 7) / 8, F), 128, smem_t, st>>>(xt, F, H, W, w3, map, out, ldo, skip_flag, skip_if);
     DAWN_LAUNCH_OK();
     return 0;
   }
@@ -770,7 +944,7 @@ int launch_init_conv_x3(const float* xt, int F, int H, int W, const float* w3, c
   const long long total = (long long)F * H * W * (Co >> 2);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  init_conv_x3_kernel<<<(int)blocks, 256, smem, st>>>(xt, F, H, W, w3, map, Co, out, ldo, ksz);
+  init_conv_x3_kernel<<<(int)blocks, 256, smem, st>>>(xt, F, H, W, w3, map, Co, out, ldo, ksz, skip_flag, skip_if);
   DAWN_LAUNCH_OK();
   return 0;
 }

@@ -89,10 +89,19 @@ int launch_sla_context(const float* qkv, int ld, int F, int P, const float* Wout
 
 // ---------------------------------------------------------------- layout / heads / init conv
 // x (C, F, H*W) channel-major -> (F, H*W, Cpad) channels-last, zero padding channels [C, Cpad)
-int launch_ncf_to_nhwc(const float* x, int C, int F, int HW, int Cpad, int c_dst0, float* out, cudaStream_t st);
+// skip_flag (device int, optional): the kernel returns at once when *skip_flag == skip_if (device-side path selection)
+int launch_ncf_to_nhwc(const float* x, int C, int F, int HW, int Cpad, int c_dst0, float* out, cudaStream_t st,
+                       const int* skip_flag = nullptr, int skip_if = 0);
+// *flag = 1 iff channels [c0, C) of x (C, F, HW) are not identical in every frame
+int launch_frame_invariance(const float* x, int c0, int C, int F, int HW, int* flag, cudaStream_t st);
+// k vertically shifted channels-last copies of one (C, H, W) frame and the reduction of the k partial maps (per-clip init-conv map)
+int launch_fea_shift_nhwc(const float* x, long long cstride, int C, int H, int W, int Cpad, int c_dst0, int k, float* out, cudaStream_t st,
+                          const int* skip_flag = nullptr, int skip_if = 0);
+int launch_map_reduce(const float* part, int nsplit, long long n, const float* bias, int Co, float* map, cudaStream_t st,
+                      const int* skip_flag = nullptr, int skip_if = 0);
 // out[f][p][co0..] = map[p][:] + conv7x7(x_t[3][F][H][W]; w3[49*3][64])   (hoisted init conv)
 int launch_init_conv_x3(const float* xt, int F, int H, int W, const float* w3, const float* map, int Co,
-                        float* out, int ldo, int ksz, cudaStream_t st);
+                        float* out, int ldo, int ksz, cudaStream_t st, const int* skip_flag = nullptr, int skip_if = 0);
 // eps[c][f][p] = head 1x1 convs: c<ng from flow features, else occlusion features   U:863, 876, 956
 int launch_heads_out(const float* hf, const float* ho, int C, int M, const float* Wf, const float* bf, int ng,
                      const float* Wo, const float* bo, int nc, float* out /*[(ng+nc)][M]*/, cudaStream_t st);

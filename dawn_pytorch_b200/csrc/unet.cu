@@ -171,6 +171,9 @@ struct dawn_unet {
   // workspace (per set_num_frames)
   int F = 0, H = 0, W = 0;
   std::vector<int> lH, lW;
+  float* MAPPART = nullptr;                    // k partial maps of the per-clip init conv (one per kernel row)
+  int* VARY = nullptr;                         // device flag of the general entry: 1 = feature channels differ between frames
+  bool prep_v1 = false;                        // DAWN_PREP_V1=1: the original per-clip table kernels
   float *X288 = nullptr, *FEA288 = nullptr, *MAP = nullptr, *XR = nullptr, *S0 = nullptr;
   std::vector<float*> bufA, bufB, CAT, DS;
   float *Y = nullptr, *A1 = nullptr, *QKV = nullptr, *O = nullptr, *ROWSTATS = nullptr, *GATES = nullptr, *WT = nullptr;
@@ -924,6 +927,34 @@ int prep_cond(dawn_unet* h, const float* cond, cudaStream_t st) {
   return 0;
 }
 
+// Per-clip constant part of the init conv from ONE frame of the feature channels (fea: channel c at
+// fea + c * cstride, H0*W0 values): kernel row ky runs as a 1 x k conv over the frame shifted by ky - pad rows ("batch" ky of
+// the contraction kernel, weight rows [ky*k*cin_pad, (ky+1)*k*cin_pad) of the packed matrix) -> k x 32 CTAs instead of 32;
+// the k partial maps are then added in a fixed order.  skip_flag: device-side path selection of the general entry.
+int init_map(dawn_unet* h, const float* fea, long long cstride, cudaStream_t st, const int* skip_flag, int skip_if) {
+  Ctx c{h, st};
+  const int H0 = h->lH[0], W0 = h->lW[0], dim = h->cfg.dim, k = h->cfg.init_kernel_size;
+  {
+    ProfScope ps(c, PC_PREP, 0, 0);
+    DAWN_TRY(launch_fea_shift_nhwc(fea, cstride, h->cfg.channels - 3, H0, W0, h->cin_pad, 3, k, h->FEA288, st, skip_flag, skip_if));
+  }
+  {
+    Act in{h->FEA288, h->cin_pad, h->cin_pad, H0, W0};
+    GemmParams p; base_params(p, in, k);                       // k "frames" = the shifted copies
+    set_weights(p, h->init_full);
+    p.ntaps = k;
+    for (int kx = 0; kx < k; ++kx) { p.dy[kx] = 0; p.dx[kx] = (signed char)(kx - k / 2); }
+    p.K = k * h->cin_pad; p.rows_per_batch = H0 * W0; p.b_batch_stride = (long long)k * h->cin_pad * h->init_full.ldb;
+    p.bias = nullptr;
+    p.Out = h->MAPPART; p.ldo = dim;
+    p.skip_flag = skip_flag; p.skip_if = skip_if;
+    ProfScope ps(c, PC_PREP, 0, 0);
+    DAWN_TRY(launch_gemm(p, EPI_PLAIN, st));
+  }
+  ProfScope ps(c, PC_PREP, 0, 0);
+  return launch_map_reduce(h->MAPPART, k, (long long)H0 * W0 * dim, h->init_full.b, dim, h->MAP, st, skip_flag, skip_if);
+}
+
 int forward_core(dawn_unet* h, const int64_t* t_dev, float* out, cudaStream_t st) {
   Ctx c{h, st};
   const int F = h->F, nlev = h->nlev, dim = h->cfg.dim;
@@ -1022,6 +1053,7 @@ int dawn_unet_create(const dawn_unet_cfg* cfg, dawn_unet** out) {
   { const char* e = getenv("DAWN_FUSED_CA"); h->use_fused_ca = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_PRESPLIT"); h->use_presplit = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_TC_CONV3"); h->use_conv3 = !(e && e[0] == '0'); }
+  { const char* e = getenv("DAWN_PREP_V1"); h->prep_v1 = (e && e[0] == '1'); }
   h->nlev = cfg->n_levels;
   h->dims.push_back(cfg->dim);
   for (int i = 0; i < cfg->n_levels; ++i) h->dims.push_back(cfg->dim * cfg->dim_mults[i]);
@@ -1150,7 +1182,9 @@ int dawn_unet_set_num_frames(dawn_unet* h, int F, int height, int width) {
   const size_t P0 = (size_t)height * width, M0 = (size_t)F * P0;
   int64_t* cnt = &h->ws_bytes;
   DAWN_TRY(dev_alloc(own, M0 * h->cin_pad, &h->X288, cnt));
-  DAWN_TRY(dev_alloc(own, P0 * h->cin_pad, &h->FEA288, cnt));
+  DAWN_TRY(dev_alloc(own, P0 * h->cin_pad * h->cfg.init_kernel_size, &h->FEA288, cnt));   // k row-shifted copies
+  DAWN_TRY(dev_alloc(own, P0 * dim * h->cfg.init_kernel_size, &h->MAPPART, cnt));
+  { float* f; DAWN_TRY(dev_alloc(own, 4, &f, cnt)); h->VARY = (int*)f; }
   DAWN_TRY(dev_alloc(own, P0 * dim, &h->MAP, cnt));
   DAWN_TRY(dev_alloc(own, M0 * 2 * dim, &h->XR, cnt));
   DAWN_TRY(dev_alloc(own, M0 * dim, &h->S0, cnt));
@@ -1245,6 +1279,9 @@ int dawn_unet_set_clip_invariants(dawn_unet* h, const float* fea, const float* c
   Ctx c{h, st};
   const int H0 = h->lH[0], W0 = h->lW[0], dim = h->cfg.dim, k = h->cfg.init_kernel_size;
   // per-clip constant part of the init conv: conv(cat[0, fea]) + bias  (linearity)
+  if (!h->prep_v1) {
+    DAWN_TRY(init_map(h, fea, (long long)H0 * W0, st, nullptr, 0));
+  } else {
   {
     ProfScope ps(c, PC_PREP, 0, 0);
     DAWN_TRY(launch_ncf_to_nhwc(fea, h->cfg.channels - 3, 1, H0 * W0, h->cin_pad, 3, h->FEA288, st));
@@ -1255,6 +1292,7 @@ int dawn_unet_set_clip_invariants(dawn_unet* h, const float* fea, const float* c
     set_weights(p, h->init_full); set_square_taps(p, k, k / 2);
     p.Out = h->MAP; p.ldo = dim;
     DAWN_TRY(c.gemm(p, EPI_PLAIN, PC_PREP));
+  }
   }
   DAWN_TRY(prep_cond(h, cond, st));
   h->have_invariants = true;
@@ -1269,17 +1307,34 @@ int dawn_unet_forward(dawn_unet* h, const float* x, const int64_t* t, const floa
   Ctx c{h, st};
   const int H0 = h->lH[0], W0 = h->lW[0], dim = h->cfg.dim, k = h->cfg.init_kernel_size;
   DAWN_TRY(prep_cond(h, cond, st));
-  h->have_invariants = false;         // MAP not refreshed by this entry
+  h->have_invariants = false;         // MAP is refreshed by this entry only when the features turn out frame-invariant
+  // Path selection on the device, no host synchronisation: one pass over x decides whether channels 3.. are the same in every
+  // frame (the reference's sampler tiles them, U:1167); both paths are enqueued and the kernels of the one not taken return
+  // at once.  invariant -> hoisted init conv (map from frame 0 + 3 live channels); varying -> full k x k conv over all channels.
+  const int* vary = nullptr;
+  if (!h->prep_v1) {
+    ProfScope ps(c, PC_MISC, 0, 4.0 * h->F * H0 * W0 * h->cfg.channels);
+    DAWN_TRY(launch_frame_invariance(x, 3, h->cfg.channels, h->F, H0 * W0, h->VARY, st));
+    vary = h->VARY;
+  }
   {
     ProfScope ps(c, PC_MISC, 0, 8.0 * h->F * H0 * W0 * h->cin_pad);
-    DAWN_TRY(launch_ncf_to_nhwc(x, h->cfg.channels, h->F, H0 * W0, h->cin_pad, 0, h->X288, st));
+    DAWN_TRY(launch_ncf_to_nhwc(x, h->cfg.channels, h->F, H0 * W0, h->cin_pad, 0, h->X288, st, vary, 0));
   }
   {
     Act in{h->X288, h->cin_pad, h->cin_pad, H0, W0};
     GemmParams p; base_params(p, in, h->F);
     set_weights(p, h->init_full); set_square_taps(p, k, k / 2);
     p.Out = h->XR + dim; p.ldo = 2 * dim;
-    DAWN_TRY(c.gemm(p, EPI_PLAIN, PC_CONV_OTHER));
+    p.skip_flag = vary; p.skip_if = 0;
+    ProfScope ps(c, PC_CONV_OTHER, 2.0 * p.M * (double)p.N * p.K, 4.0 * p.M * ((double)p.Cin + p.N));
+    DAWN_TRY(launch_gemm(p, EPI_PLAIN, st));      // Cin = 288 is not a tcgen05 shape: always the mma.sync kernel (it has the skip flag)
+  }
+  if (vary) {
+    DAWN_TRY(init_map(h, x + (size_t)3 * h->F * H0 * W0, (long long)h->F * H0 * W0, st, vary, 1));
+    const double k2 = (double)k * k;
+    ProfScope ps(c, PC_MISC, 2.0 * h->F * H0 * W0 * dim * 3 * k2, 4.0 * h->F * H0 * W0 * (dim + 3));
+    DAWN_TRY(launch_init_conv_x3(x, h->F, H0, W0, h->init_w3, h->MAP, dim, h->XR + dim, 2 * dim, k, st, vary, 1));
   }
   return forward_core(h, t, out, st);
 }

@@ -239,3 +239,34 @@ def test_handle_ddim_step_equals_plain_entry_unsharded():
     s = torch.quantile(x0.abs(), 0.9).clamp(min=1.0)
     ref = x0.clamp(-s, s) / s * 0.9 + 0.3 * e + 0.2 * nz
     assert (xa.cpu() - ref).abs().max().item() < 2e-6
+
+
+def test_general_entry_selects_its_init_conv_path_on_the_device():
+    """Drop-in entry forward(x275): frame-invariant feature channels (what the reference's sampler passes, U:1167) take the
+    hoisted init conv, frame-varying ones the full 7x7 conv over all 275 channels — chosen by a device-side flag, both
+    against the oracle on the same inputs."""
+    net = G.cuda_net()
+    x, t, cond, x_t, fea = G.clip("odd")
+    with torch.no_grad():
+        ref_inv = O.unet_forward(G.synth_sd(), O.UnetCfg(), x, t, cond)
+    out_inv = run(net, x, t, cond)
+    assert G.over_tol(out_inv, ref_inv) <= 1.0
+    xv = x.clone()
+    F = x.shape[2]
+    ramp = torch.linspace(-0.5, 0.5, F).view(1, 1, F, 1, 1)
+    xv[:, 3:] = torch.relu(xv[:, 3:] + ramp)                  # features now differ from frame to frame
+    with torch.no_grad():
+        ref_var = O.unet_forward(G.synth_sd(), O.UnetCfg(), xv, t, cond)
+    out_var = run(net, xv, t, cond)
+    r = G.over_tol(out_var, ref_var)
+    print(f"general entry, frame-varying features: {r:.3f} x tol; invariant: {G.over_tol(out_inv, ref_inv):.3f}")
+    assert r <= 1.0
+    assert (out_var - out_inv).abs().max().item() > 1e-2
+    # a single differing value in the last frame must flip the path as well
+    x1 = x.clone()
+    x1[0, 274, F - 1, -1, -1] += 1.0
+    with torch.no_grad():
+        ref1 = O.unet_forward(G.synth_sd(), O.UnetCfg(), x1, t, cond)
+    assert G.over_tol(run(net, x1, t, cond), ref1) <= 1.0
+    # and back: the invariant clip again (the flag is re-evaluated on every call)
+    assert G.over_tol(run(net, x, t, cond), ref_inv) <= 1.0
