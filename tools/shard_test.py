@@ -1,4 +1,5 @@
-"""2+ GPUs (torchrun): exact frame sharding of one clip vs the reference golden / the unsharded CUDA path."""
+"""2+ GPUs (torchrun): exact frame sharding of one clip vs the reference golden / the unsharded CUDA path.
+   torchrun ... tools/shard_test.py [forward] [ddim] [ddim_graph]     (default: forward ddim)"""
 import os
 import sys
 
@@ -12,7 +13,7 @@ from oracle import weights as W            # noqa: E402
 from tests import gpu_common as G          # noqa: E402
 
 
-def sampler_case(net, rank, world, dev):
+def sampler_case(net, rank, world, dev, graph_modes):
     """Row a16 under sharding: 3 DDIM steps (first, middle, last of the 20-step schedule) on a frame-sharded clip — clip-wide
     quantile through all-reduced radix select, per-rank slice of one clip-wide noise tensor — vs the single-GPU sampler."""
     from dawn_pytorch_b200 import DynamicNfGaussianDiffusion, DynamicNfUnet3D
@@ -34,7 +35,7 @@ def sampler_case(net, rank, world, dev):
     net.init_shard(Fl, h, w, dev)
     assert net.shard_info() == (rank, world)
     D.update_num_frames(Fl)
-    for use_graph in (False, True):
+    for use_graph in graph_modes:
         out = D.ddim_sample(fea.to(dev), (1, 3, Fl, h, w), cond=cond[:, lo:lo + Fl].contiguous().to(dev), pairs=pairs,
                             noise_fn=lambda k, shp: noise_global(k)[:, lo:lo + Fl].reshape(shp).clone(), use_graph=use_graph)[0].clone()
         parts = [torch.empty_like(out) for _ in range(world)]
@@ -65,7 +66,8 @@ def main():
     net = DynamicNfUnet3D(**G.CTOR).eval()
     net.load_state_dict(G.synth_sd(), strict=True)
     net = net.to(dev)
-    cases = [("band", 96, 8, 8, 952, True), ("shardbig", 80 * world, 32, 32, 500, False)]
+    what = set(sys.argv[1:]) or {"forward", "ddim"}
+    cases = [("band", 96, 8, 8, 952, True), ("shardbig", 80 * world, 32, 32, 500, False)] if "forward" in what else []
     for name, Fg, h, w, t, has_golden in cases:
         if Fg % world or Fg // world < 40:
             continue
@@ -101,7 +103,9 @@ def main():
                   f"  max|d| {(full[0] - one.cpu()).abs().max():.2e};  sharded step {ms:.2f} ms", flush=True)
             del net1
         dist.barrier()
-    sampler_case(net, rank, world, dev)
+    modes = ([False] if "ddim" in what else []) + ([True] if "ddim_graph" in what else [])
+    if modes:
+        sampler_case(net, rank, world, dev, modes)
     dist.destroy_process_group()
 
 
