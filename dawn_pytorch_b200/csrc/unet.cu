@@ -528,6 +528,8 @@ enum ProfCat : int {
   PC_CA_RSTD,        // cross-attention output LayerNorm via Gram form
   PC_MISC,           // time MLP, FiLM, init conv (3 ch), heads, layout
   PC_PREP,           // per-clip tables
+  PC_TEMPORAL_L0,    // fused per-pixel temporal attention at level 0 (the dominant kernel: bench.py's roofline object)
+  PC_CONV3_L0,       // halo-tile 3x3 conv, dim -> dim channels at level 0
   PC_COUNT
 };
 static_assert(PC_COUNT <= DAWN_PROF_NCAT, "increase DAWN_PROF_NCAT");
@@ -612,7 +614,8 @@ int conv_same(Ctx& c, const Act& in, const ConvW& w, int k, const Act& out, int 
   set_weights(p, w); set_square_taps(p, k, k / 2);
   p.Out = out.p; p.ldo = out.ld;
   if (stat_slot >= 0) { p.stats = c.h->STATS + 16 * stat_slot; p.cpg = w.N / 8; }
-  return c.gemm(p, EPI_PLAIN, k == 3 ? PC_CONV3 : PC_CONV_OTHER);
+  const bool l0 = in.H == c.h->lH[0] && in.C == c.h->cfg.dim && w.N == c.h->cfg.dim;
+  return c.gemm(p, EPI_PLAIN, k == 3 ? (l0 ? PC_CONV3_L0 : PC_CONV3) : PC_CONV_OTHER);
 }
 
 // GroupNorm statistics span all frames of the clip: with frame sharding the 16 partial sums are all-reduced (fp64)
@@ -732,7 +735,7 @@ int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const st
     a.inv_wscale = w.f_inv_wscale; a.inv_oscale = w.f_inv_oscale;
     double pairs = 0;
     for (int i = hl; i < hl + F; ++i) pairs += std::min(Fe - 1, i + a.band) - std::max(0, i - a.band) + 1;
-    ProfScope ps(c, PC_ATTN_CORE, 2.0 * Me * x.C * 768 + 4.0 * 32 * 8 * P * pairs + 2.0 * F * P * 256 * x.C,
+    ProfScope ps(c, x.H == h->lH[0] ? PC_TEMPORAL_L0 : PC_ATTN_CORE, 2.0 * Me * x.C * 768 + 4.0 * 32 * 8 * P * pairs + 2.0 * F * P * 256 * x.C,
                  4.0 * (Me + 2.0 * F * P) * x.C);
     DAWN_TRY(launch_temporal_fused(a, c.st));
     return tap(c, name, dst);
@@ -1034,7 +1037,7 @@ int forward_core(dawn_unet* h, const int64_t* t_dev, float* out, cudaStream_t st
 extern "C" {
 
 const char* dawn_last_error(void) { return g_last_error.c_str(); }
-const char* dawn_build_info(void) { return "dawn_unet sm_100a; contraction path: mma.sync 3xTF32 (+tcgen05 bf16x3 where enabled)"; }
+const char* dawn_build_info(void) { return "dawn_unet sm_100a; contractions: tcgen05 kind::f16 FP16x3 (TMEM accumulators) + mma.sync m16n8k16 FP16x3 fused attention kernels; fallback mma.sync 3xTF32"; }
 
 int dawn_unet_create(const dawn_unet_cfg* cfg, dawn_unet** out) {
   DAWN_CHECK(cfg && out, "null argument");

@@ -234,7 +234,9 @@ class Unet3D(nn.Module):
         return super()._apply(fn, *a, **k)
 
     def __del__(self):
-        h, self._handle = getattr(self, "_handle", None), None
+        # plain dict access: nn.Module.__setattr__/__getattr__ may already be torn down at interpreter shutdown
+        h = self.__dict__.get("_handle")
+        self.__dict__["_handle"] = None
         if h is not None:
             try:
                 lib.dawn_unet_destroy(h)

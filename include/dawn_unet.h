@@ -93,7 +93,9 @@ int dawn_unet_tap_shape(dawn_unet* h, const char* name, int* C, int* hl, int* wl
  * read() synchronises on the last event and returns, per category, accumulated milliseconds, algorithmic
  * flops (2*MAC, counted once — not the 3 split-precision passes), algorithmic bytes and launch counts.
  * Arrays must hold DAWN_PROF_NCAT entries.  Category order: conv3x3, conv_other, qkv_proj, out_proj,
- * ca_gate, gn_hcond, attn_core, sla_context, gn_apply, rowstats, ca_rstd, misc, prep. */
+ * ca_gate, gn_hcond, attn_core, sla_context, gn_apply, rowstats, ca_rstd, misc, prep, temporal_fused_l0 (the fused
+ * temporal attention launches at level 0, not counted in attn_core), conv3x3_l0 (dim -> dim 3x3 convs at level 0, not
+ * counted in conv3x3). */
 #define DAWN_PROF_NCAT 16
 int dawn_unet_profile_enable(dawn_unet* h, int on);
 int dawn_unet_profile_read(dawn_unet* h, double* ms, double* flops, double* bytes, int64_t* count);

@@ -117,3 +117,51 @@ def test_sharded_dynamic_threshold_equals_torch_quantile_world2():
     for s, qv, ref, ref_s in q.get(timeout=5):
         assert qv == ref, (qv, ref)
         assert s == ref_s
+
+
+def _worker3(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import json
+        from oracle import sharded as S
+        from oracle import unet_oracle as O
+        from oracle import weights as W
+        with open(os.path.join(ROOT, "tests", "golden", "state_dict_schema.json")) as f:
+            schema = json.load(f)
+        sd = W.synth_state_dict([(n, tuple(s)) for n, s in schema["entries"]])
+        Fg, h, w, t = 120, 8, 8, 476                      # 40 frames per rank == the window: the middle rank has BOTH halos
+        x_t, fea, cond = W.synth_inputs("band3", Fg, h, w)
+        x = torch.cat([x_t, fea.unsqueeze(2).expand(-1, -1, Fg, -1, -1)], dim=1)
+        Fl = Fg // world
+        lo = rank * Fl
+        with torch.no_grad():
+            out = S.sharded_unet_forward(sd, O.UnetCfg(), x[:, :, lo:lo + Fl].contiguous(), torch.full((1,), t),
+                                         cond[:, lo:lo + Fl].contiguous(), Fg)
+        parts = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(parts, out)
+        if rank == 0:
+            with torch.no_grad():
+                ref = O.unet_forward(sd, O.UnetCfg(), x, torch.full((1,), t), cond)
+            full = torch.cat(parts, dim=2)
+            q.put(float(((full - ref).abs() / (1e-4 + 1e-3 * ref.abs())).max()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_frame_sharded_oracle_interior_rank_world3():
+    """world_size 3, 40 frames per rank: rank 1 exchanges halos on both sides (the N >= 3 case of SURVEY 8e)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker3, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    over_tol = q.get(timeout=5)
+    print("sharded (world 3) vs unsharded oracle: x tol =", over_tol)
+    assert over_tol < 0.5

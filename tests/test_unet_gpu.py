@@ -270,3 +270,39 @@ def test_general_entry_selects_its_init_conv_path_on_the_device():
     assert G.over_tol(run(net, x1, t, cond), ref1) <= 1.0
     # and back: the invariant clip again (the flag is re-evaluated on every call)
     assert G.over_tol(run(net, x, t, cond), ref_inv) <= 1.0
+
+
+@pytest.mark.parametrize("tag,F,h,w,t", [
+    ("edge_f1", 1, 8, 8, 999),          # a single frame: every temporal softmax has one key
+    ("edge_f40", 40, 8, 16, 0),         # F == window, non-square latent (w = 2h), t = 0
+    ("edge_f41", 41, 16, 8, 523),       # first length at which the band excludes a pair (|i-j| = 41 > 40), h = 2w
+    ("edge_f81", 81, 8, 8, 47),         # 2*window + 1: the centre frame sees the whole clip, the ends half of it
+    ("edge_f17x24", 17, 24, 24, 300),   # latent side not a power of two (24 = 8*3): level sizes 24, 12, 6, 3
+])
+def test_edge_geometries_against_oracle(tag, F, h, w, t):
+    """Ragged / extreme geometries the fused kernels special-case (frame counts around the +-40 window and the 16-frame MMA
+    tile, non-square and non-power-of-two latents) against the CPU oracle on the same seeded inputs."""
+    net = G.cuda_net()
+    x, tt, cond, _, _ = G.clip(tag, F, h, w, t)
+    out = run(net, x, tt, cond)
+    with torch.no_grad():
+        ref = O.unet_forward(G.synth_sd(), O.UnetCfg(), x, tt, cond)
+    r = G.over_tol(out, ref)
+    print(f"{tag}: {r:.3f} x tol, max|d| {(out - ref).abs().max():.2e}")
+    assert r <= 1.0
+
+
+def test_other_window_width_against_oracle():
+    """win_width is a constructor argument (FD:155): an 8-frame window on a 23-frame clip."""
+    from dawn_pytorch_b200 import DynamicNfUnet3D
+    ctor = dict(G.CTOR, win_width=8)
+    net = DynamicNfUnet3D(**ctor).eval()
+    net.load_state_dict(G.synth_sd(), strict=True)
+    net = net.cuda()
+    x, t, cond, _, _ = G.clip("odd")
+    out = run(net, x, t, cond)
+    with torch.no_grad():
+        ref = O.unet_forward(G.synth_sd(), O.UnetCfg(win_width=8), x, t, cond)
+        ref40 = O.unet_forward(G.synth_sd(), O.UnetCfg(), x, t, cond)
+    assert G.over_tol(out, ref) <= 1.0
+    assert (ref - ref40).abs().max().item() > 1e-3          # the window really matters on this clip
