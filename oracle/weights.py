@@ -96,3 +96,47 @@ def synth_inputs(tag: str, F: int, h: int, w: int, cond_dim: int = 1032, fea_ch:
     fea = torch.from_numpy(np.maximum(pseudo_normal(f"{tag}/fea", (1, fea_ch, h, w)), 0))
     cond = torch.from_numpy(pseudo_normal(f"{tag}/cond", (1, F, cond_dim)))
     return x_t, fea, cond
+
+
+# ----------------------------------------------------------------------------- LFG flow decoder (oracle/lfg_oracle.py)
+def lfg_synth_value(name: str, shape) -> np.ndarray:
+    """Synthetic Generator weights (LFG/modules/generator.py): He-uniform convs so that 14 conv + ReLU layers keep O(1)
+    activations, BatchNorm affine terms and running statistics away from their trivial values (running_var stays positive)."""
+    shape = tuple(int(s) for s in shape)
+    leaf = name.split('.')[-1]
+    if leaf == 'num_batches_tracked':
+        return np.zeros((), dtype=np.int64)
+    if leaf == 'running_mean':
+        return symmetric(name, shape, 0.2)
+    if leaf == 'running_var':
+        return np.float32(1.0) + symmetric(name, shape, 0.3)
+    if '.norm' in name and leaf == 'weight':
+        return np.float32(1.0) + symmetric(name, shape, 0.2)
+    if '.norm' in name and leaf == 'bias':
+        return symmetric(name, shape, 0.1)
+    if leaf == 'bias':
+        return symmetric(name, shape, 0.05)
+    if leaf == 'weight' and len(shape) == 4:
+        fan_in = int(np.prod(shape[1:]))
+        gain = 1.0 if name.startswith('final') else math.sqrt(2.0)
+        return symmetric(name, shape, gain * math.sqrt(3.0 / fan_in))
+    raise ValueError(f"no synthetic LFG rule for {name} {shape}")
+
+
+def lfg_synth_state_dict(schema):
+    import torch
+    return {n: torch.from_numpy(np.ascontiguousarray(lfg_synth_value(n, s))) for n, s in schema}
+
+
+def lfg_synth_inputs(tag: str, F: int, H: int, W: int, h: int, w: int):
+    """source image in [0, 1] (1, 3, H, W); sampling grid = identity + smooth-ish random offsets, some of it outside [-1, 1]
+    (zero padding is exercised); occlusion map in [0, 1] (F, 1, h, w) — what sample_one_video feeds forward_with_flow (FD:372-383)."""
+    import torch
+    src = torch.from_numpy(uniform01(f"{tag}/src", 3 * H * W).reshape(1, 3, H, W))
+    ys = (np.arange(h, dtype=np.float32) + np.float32(0.5)) / np.float32(h) * np.float32(2) - np.float32(1)
+    xs = (np.arange(w, dtype=np.float32) + np.float32(0.5)) / np.float32(w) * np.float32(2) - np.float32(1)
+    gx, gy = np.meshgrid(xs, ys)
+    ident = np.stack([gx, gy], axis=-1)[None].astype(np.float32)
+    flow = ident + symmetric(f"{tag}/flow", (F, h, w, 2), 0.35)
+    occ = uniform01(f"{tag}/occ", F * h * w).reshape(F, 1, h, w)
+    return src, torch.from_numpy(flow.astype(np.float32)), torch.from_numpy(occ)
