@@ -2,3 +2,4 @@
 Python module interface (DynamicNfUnet3D / DynamicNfGaussianDiffusion)."""
 from .unet import DynamicNfUnet3D, Unet3D  # noqa: F401
 from .diffusion import DynamicNfGaussianDiffusion, GaussianDiffusion  # noqa: F401
+from .lfg import Generator as LfgGenerator  # noqa: F401

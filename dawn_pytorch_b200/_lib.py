@@ -15,6 +15,12 @@ class DawnUnetCfg(ctypes.Structure):
                 ("init_kernel_size", ctypes.c_int), ("win_width", ctypes.c_int)]
 
 
+class DawnLfgCfg(ctypes.Structure):
+    """include/dawn_lfg.h: dawn_lfg_cfg"""
+    _fields_ = [("num_channels", ctypes.c_int), ("block_expansion", ctypes.c_int), ("max_features", ctypes.c_int),
+                ("num_down_blocks", ctypes.c_int), ("num_bottleneck_blocks", ctypes.c_int), ("skips", ctypes.c_int)]
+
+
 class DawnError(RuntimeError):
     pass
 
@@ -54,6 +60,22 @@ def _load():
     lib.dawn_unet_ddim_step.argtypes = [vp, fp, fp, fp, ctypes.c_int64] + [ctypes.c_float] * 6 + [vp, vp]
     lib.dawn_unet_sampler_capture.argtypes = [vp, fp, fp, fp, vp, ctypes.POINTER(ctypes.c_float), ctypes.c_int, ctypes.c_float, vp]
     lib.dawn_unet_sampler_launch.argtypes = [vp, vp]
+    ip = ctypes.POINTER(ctypes.c_int)
+    lib.dawn_lfg_create.argtypes = [ctypes.POINTER(DawnLfgCfg), ctypes.POINTER(vp)]
+    lib.dawn_lfg_destroy.argtypes = [vp]
+    lib.dawn_lfg_destroy.restype = None
+    lib.dawn_lfg_set_param.argtypes = [vp, cp, fp, i64p, ctypes.c_int]
+    lib.dawn_lfg_commit_params.argtypes = [vp]
+    lib.dawn_lfg_set_geometry.argtypes = [vp] + [ctypes.c_int] * 5
+    lib.dawn_lfg_set_source.argtypes = [vp, fp, vp]
+    lib.dawn_lfg_get_fea.argtypes = [vp, fp, vp]
+    lib.dawn_lfg_decode.argtypes = [vp, fp, fp, fp, fp, vp]
+    lib.dawn_lfg_decode_sample.argtypes = [vp, fp, fp, fp, vp]
+    lib.dawn_lfg_read_tap.argtypes = [vp, cp, fp, ip, ip, ip, vp]
+    lib.dawn_lfg_last_launch_count.argtypes = [vp]
+    lib.dawn_lfg_last_launch_count.restype = ctypes.c_int64
+    lib.dawn_lfg_workspace_bytes.argtypes = [vp]
+    lib.dawn_lfg_workspace_bytes.restype = ctypes.c_int64
     lib.dawn_last_error.restype = cp
     lib.dawn_build_info.restype = cp
     return lib
@@ -67,6 +89,10 @@ EXPORTS = ["dawn_unet_create", "dawn_unet_destroy", "dawn_unet_set_param", "dawn
            "dawn_unet_profile_enable", "dawn_unet_profile_read", "dawn_unet_last_launch_count", "dawn_unet_workspace_bytes", "dawn_ddim_step", "dawn_unet_ddim_step", "dawn_unet_sampler_capture", "dawn_unet_sampler_launch",
            "dawn_selftest_tc_gemm", "dawn_selftest_attention", "dawn_last_error", "dawn_build_info"]
 
+
+LFG_EXPORTS = ["dawn_lfg_create", "dawn_lfg_destroy", "dawn_lfg_set_param", "dawn_lfg_commit_params", "dawn_lfg_set_geometry",
+               "dawn_lfg_set_source", "dawn_lfg_get_fea", "dawn_lfg_decode", "dawn_lfg_decode_sample", "dawn_lfg_read_tap",
+               "dawn_lfg_last_launch_count", "dawn_lfg_workspace_bytes"]
 
 PROF_CATS = ["conv3x3", "conv_other", "qkv_proj", "out_proj", "ca_gate", "gn_hcond", "attn_core", "sla_context",
              "gn_apply", "rowstats", "ca_rstd", "misc", "prep", "temporal_fused_l0", "conv3x3_l0"]

@@ -88,3 +88,53 @@ def test_rel_bias_table_matches_oracle(synth_sd):
         for j in range(max(0, i - 40), min(200, i + 41)):
             assert torch.equal(full[:, i, j], tab[:, j - i + 40])
     assert torch.equal(O.sinusoidal(torch.tensor([500]), 64)[0, :32], torch.sin(500 * _time_freqs(64)))
+
+
+# ----------------------------------------------------------------------------- LFG flow decoder boundary (include/dawn_lfg.h)
+LFG_CTOR = dict(num_channels=3, num_regions=10, block_expansion=64, max_features=512, num_down_blocks=2, num_bottleneck_blocks=6,
+                pixelwise_flow_predictor_params={"block_expansion": 64}, skips=True, revert_axis_swap=True)
+
+
+def test_lfg_library_exports_every_declared_symbol():
+    from dawn_pytorch_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "dawn_lfg.h")).read()
+    declared = set(re.findall(r"\b(dawn_lfg_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.LFG_EXPORTS)
+    for sym in declared:
+        assert hasattr(_lib.lib, sym), f"{sym} declared in include/dawn_lfg.h but not exported"
+
+
+def test_lfg_state_dict_schema_equals_reference_decode_path(golden_dir):
+    import json
+    from dawn_pytorch_b200 import LfgGenerator
+    from oracle import weights as W
+    with open(os.path.join(golden_dir, "lfg_state_dict_schema.json")) as f:
+        sch = json.load(f)
+    g = LfgGenerator(**LFG_CTOR)
+    mine = [(k, list(v.shape)) for k, v in g.state_dict().items()]
+    assert mine == [(k, list(s)) for k, s in sch["entries"]]          # same keys, shapes and registration order (dumped from the reference)
+    sd = W.lfg_synth_state_dict([(n, tuple(s)) for n, s in sch["entries"]])
+    sd["pixelwise_flow_predictor.hourglass.encoder.down_blocks.0.conv.weight"] = torch.zeros(4)     # training-only entries of the checkpoint
+    res = g.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert not g.training
+    with pytest.raises(NotImplementedError):
+        g.train()
+
+
+def test_lfg_cpu_tensors_fail_loudly_and_argument_checks():
+    from dawn_pytorch_b200 import LfgGenerator, _lib
+    g = LfgGenerator(**LFG_CTOR)
+    with pytest.raises(_lib.DawnError):
+        g.forward_with_flow(torch.rand(1, 3, 64, 64), torch.zeros(2, 16, 16, 2), torch.zeros(2, 1, 16, 16))
+    lib = _lib.lib
+    cfg = _lib.DawnLfgCfg()
+    cfg.num_channels, cfg.block_expansion, cfg.max_features = 3, 64, 512
+    cfg.num_down_blocks, cfg.num_bottleneck_blocks, cfg.skips = 2, 6, 1
+    h = ctypes.c_void_p()
+    assert lib.dawn_lfg_create(ctypes.byref(cfg), ctypes.byref(h)) == 0
+    assert lib.dawn_lfg_set_geometry(h, 4, 64, 64, 16, 16) == -1          # wrong call order is an error, not a crash
+    assert b"commit_params" in lib.dawn_last_error()
+    lib.dawn_lfg_destroy(h)
+    cfg.num_channels = 4
+    assert lib.dawn_lfg_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
