@@ -72,6 +72,7 @@ def _load():
     lib.dawn_lfg_decode.argtypes = [vp, fp, fp, fp, fp, vp]
     lib.dawn_lfg_decode_sample.argtypes = [vp, fp, fp, fp, vp]
     lib.dawn_lfg_read_tap.argtypes = [vp, cp, fp, ip, ip, ip, vp]
+    lib.dawn_conv3x3_s2_relu.argtypes = [fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp, fp, ctypes.c_int, fp, vp]
     lib.dawn_lfg_last_launch_count.argtypes = [vp]
     lib.dawn_lfg_last_launch_count.restype = ctypes.c_int64
     lib.dawn_lfg_workspace_bytes.argtypes = [vp]
@@ -93,6 +94,7 @@ EXPORTS = ["dawn_unet_create", "dawn_unet_destroy", "dawn_unet_set_param", "dawn
 LFG_EXPORTS = ["dawn_lfg_create", "dawn_lfg_destroy", "dawn_lfg_set_param", "dawn_lfg_commit_params", "dawn_lfg_set_geometry",
                "dawn_lfg_set_source", "dawn_lfg_get_fea", "dawn_lfg_decode", "dawn_lfg_decode_sample", "dawn_lfg_read_tap",
                "dawn_lfg_last_launch_count", "dawn_lfg_workspace_bytes"]
+MISC_EXPORTS = ["dawn_conv3x3_s2_relu"]
 
 PROF_CATS = ["conv3x3", "conv_other", "qkv_proj", "out_proj", "ca_gate", "gn_hcond", "attn_core", "sla_context",
              "gn_apply", "rowstats", "ca_rstd", "misc", "prep", "temporal_fused_l0", "conv3x3_l0"]

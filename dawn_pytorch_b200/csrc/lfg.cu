@@ -500,6 +500,12 @@ int dawn_lfg_read_tap(dawn_lfg* h, const char* name, float* dst, int* C, int* Hl
   return launch_lfg_hwc_to_chw(src, *C, *C, (long long)h->F * *Hl * *Wl, dst, (cudaStream_t)stream);
 }
 
+// one layer of Face_loc_Encoder (FD:39-50): relu(conv3x3 stride 2 pad 1); all device pointers, weights as nn.Conv2d stores them
+int dawn_conv3x3_s2_relu(const float* x, int Ci, int H, int W, const float* weight, const float* bias, int Co, float* out, void* stream) {
+  LFG_CHECK(x && weight && bias && out && Ci >= 1 && Co >= 1 && H >= 1 && W >= 1, "dawn_conv3x3_s2_relu: bad argument");
+  return launch_conv3x3_s2_relu(x, Ci, H, W, weight, bias, Co, out, (cudaStream_t)stream);
+}
+
 int64_t dawn_lfg_last_launch_count(dawn_lfg* h) { return h ? h->launches : 0; }
 int64_t dawn_lfg_workspace_bytes(dawn_lfg* h) { return h ? h->ws_bytes : 0; }
 

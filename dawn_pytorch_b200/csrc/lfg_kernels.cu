@@ -241,6 +241,30 @@ __global__ void __launch_bounds__(FT * FT) final_conv_kernel(const float* __rest
   for (int c = 0; c < 3; ++c) prediction[obase + c * HWs] = o[c];
 }
 
+// Face_loc_Encoder layer (FD:39-50): out = relu(conv3x3 stride 2, pad 1 (x) + b), planar (C, H, W) tensors, a handful of channels.
+// One thread per output element; runs twice per clip on a (1, H, W) mask.
+__global__ void conv3x3_s2_relu_kernel(const float* __restrict__ x, int Ci, int H, int W, const float* __restrict__ wgt,
+                                       const float* __restrict__ bias, int Co, float* __restrict__ out) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;                     // floor((H + 2 - 3) / 2) + 1
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Co * Ho * Wo) return;
+  const int xo = (int)(idx % Wo), yo = (int)((idx / Wo) % Ho), co = (int)(idx / ((long long)Wo * Ho));
+  float acc = bias[co];
+  for (int ci = 0; ci < Ci; ++ci)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = 2 * yo + ky - 1;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = 2 * xo + kx - 1;
+        if (ix < 0 || ix >= W) continue;
+        acc += x[((size_t)ci * H + iy) * W + ix] * wgt[((co * Ci + ci) * 3 + ky) * 3 + kx];
+      }
+    }
+  out[idx] = fmaxf(acc, 0.f);
+}
+
 inline int grid_for(long long n, int threads, int cap) {
   long long b = (n + threads - 1) / threads;
   return (int)std::max<long long>(1, std::min<long long>(b, cap));
@@ -290,6 +314,12 @@ int launch_lfg_chw_to_hwc(const float* x, int C, int HW, int Cpad, float* out, c
 int launch_lfg_hwc_to_chw(const float* x, int ld, int C, long long M, float* out, cudaStream_t st) {
   const long long n = M * C;
   hwc_to_chw_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(x, ld, C, M, out);
+  DAWN_LAUNCH_OK();
+  return 0;
+}
+int launch_conv3x3_s2_relu(const float* x, int Ci, int H, int W, const float* wgt, const float* bias, int Co, float* out, cudaStream_t st) {
+  const long long n = (long long)Co * ((H + 1) / 2) * ((W + 1) / 2);
+  conv3x3_s2_relu_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(x, Ci, H, W, wgt, bias, Co, out);
   DAWN_LAUNCH_OK();
   return 0;
 }

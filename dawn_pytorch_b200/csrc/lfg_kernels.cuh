@@ -28,6 +28,9 @@ int launch_lfg_relu_avgpool2(const float* x, int H, int W, int C, float* out, cu
 int launch_lfg_chw_to_hwc(const float* x, int C, int HW, int Cpad, float* out, cudaStream_t st);
 int launch_lfg_hwc_to_chw(const float* x, int ld, int C, long long M, float* out, cudaStream_t st);
 
+// out (Co, ceil(H/2), ceil(W/2)) = relu(conv3x3 stride 2 pad 1 of x (Ci, H, W) + bias); wgt (Co, Ci, 3, 3) as nn.Conv2d stores it
+int launch_conv3x3_s2_relu(const float* x, int Ci, int H, int W, const float* wgt, const float* bias, int Co, float* out, cudaStream_t st);
+
 // final 7x7 conv (Cin -> 3) + sigmoid + the last apply_optical with the source image (generator.py:163-167):
 //   prediction[f] = grid_sample(source, flow_f^) * occ_f^ + sigmoid(conv(x_f)) * (1 - occ_f^)     written as (F, 3, H, W)
 //   deformed[f]   = grid_sample(source, flow_f^)                                                  (optional, generator.py:152)

@@ -7,7 +7,7 @@
  * Here the source-image encoder (first + down blocks, generator.py:140-146) runs once per clip and all frames are decoded as
  * one batch.  Plain pointers and sizes; one handle per GPU, not thread-safe, stream-ordered, no host synchronisation inside
  * set_source / decode.  All tensors fp32.  Return: 0 ok, -1 bad argument / order / unsupported configuration, -2 CUDA error;
- * text through dawn_last_error() (include/dawn_unet.h).
+ * text through dawn_last_error, declared in include/dawn_unet.h.
  */
 #ifndef DAWN_LFG_H_
 #define DAWN_LFG_H_
@@ -58,6 +58,10 @@ int dawn_lfg_decode_sample(dawn_lfg* h, const float* sample, float* prediction, 
 /* debugging / sub-module parity: copy of an internal activation of the last decode as (C, frames, Hl, Wl):
  * "bottleneck", "up0", "up1" (names as in oracle/lfg_oracle.py taps).  Writes C, Hl, Wl; dst may be NULL to query the shape. */
 int dawn_lfg_read_tap(dawn_lfg* h, const char* name, float* dst, int* C, int* Hl, int* Wl, void* stream);
+
+/* one layer of Face_loc_Encoder (FD:39-50), the per-clip face-box embedding fed to the UNet next to the source features:
+ * out (Co, ceil(H/2), ceil(W/2)) = relu(conv3x3 stride 2 pad 1 of x (Ci, H, W) + bias).  All device pointers; weight (Co, Ci, 3, 3). */
+int dawn_conv3x3_s2_relu(const float* x, int Ci, int H, int W, const float* weight, const float* bias, int Co, float* out, void* stream);
 
 int64_t dawn_lfg_last_launch_count(dawn_lfg* h);
 int64_t dawn_lfg_workspace_bytes(dawn_lfg* h);

@@ -98,8 +98,8 @@ LFG_CTOR = dict(num_channels=3, num_regions=10, block_expansion=64, max_features
 def test_lfg_library_exports_every_declared_symbol():
     from dawn_pytorch_b200 import _lib
     hdr = open(os.path.join(ROOT, "include", "dawn_lfg.h")).read()
-    declared = set(re.findall(r"\b(dawn_lfg_[a-z0-9_]+)\s*\(", hdr))
-    assert declared == set(_lib.LFG_EXPORTS)
+    declared = set(re.findall(r"\b(dawn_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.LFG_EXPORTS) | set(_lib.MISC_EXPORTS)
     for sym in declared:
         assert hasattr(_lib.lib, sym), f"{sym} declared in include/dawn_lfg.h but not exported"
 
@@ -138,3 +138,22 @@ def test_lfg_cpu_tensors_fail_loudly_and_argument_checks():
     lib.dawn_lfg_destroy(h)
     cfg.num_channels = 4
     assert lib.dawn_lfg_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+
+
+def test_flow_diffusion_wrapper_structure_and_bbox_mask(golden_dir):
+    """N3: the consumer wrapper keeps the reference's attribute names / state_dict layout (UVG:527-528 loads `diffusion`),
+    and its face-box mask equals the reference's (value from the real `generate_bbox_mask`, oracle/make_golden_e2e.py)."""
+    import numpy as np
+    from dawn_pytorch_b200 import FlowDiffusion
+    m = FlowDiffusion(sampling_timesteps=20, pose_dim=6)
+    assert len(m.diffusion.state_dict()) == 912 and len(m.unet.state_dict()) == 900
+    assert len(m.generator.state_dict()) == 121 and list(m.face_loc_emb.state_dict()) == ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias"]
+    m.update_num_frames(123)
+    assert m.unet.num_frames == 123 and m.diffusion.num_frames == 123
+    g = np.load(os.path.join(golden_dir, "e2e_sample_one_video.npz"))
+    bbox = torch.tensor([[20., 44., 16., 50., 64., 64.]]).unsqueeze(-1).repeat(1, 1, 8)
+    mask = m.generate_bbox_mask(bbox, size=64)
+    assert mask.shape == (1, 1, 64, 64) and float(mask.sum()) == float(g["bbox_mask_sum"])
+    assert bbox[0, 0, 0] == 20.0                                  # the caller's tensor is not modified (the reference scales it in place)
+    with pytest.raises(NotImplementedError):
+        FlowDiffusion(is_train=True)
