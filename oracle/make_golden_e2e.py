@@ -19,10 +19,8 @@ from torch import nn
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(HERE, 'shims'))
-sys.path.insert(0, '/root/reference')
-warnings.filterwarnings("ignore")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 from oracle import lfg_oracle as L       # noqa: E402
 from oracle import weights as W          # noqa: E402
@@ -59,6 +57,11 @@ def face_sd():
 
 def main():
     import json
+    # the shims and the reference tree are only put on the path when goldens are generated: tests import this module for
+    # e2e_inputs() / face_sd() and must not see the shim packages
+    sys.path.insert(0, os.path.join(HERE, 'shims'))
+    sys.path.insert(0, '/root/reference')
+    warnings.filterwarnings("ignore")
     FD = importlib.import_module(FD_MOD)
     U = importlib.import_module(U_MOD)
     from LFG.modules.generator import Generator

@@ -15,7 +15,6 @@ from tests import gpu_common as G
 pytestmark = pytest.mark.gpu            # validated on B200: grid 4.2e-6, frames 0.154 x tol (profiles/r1_o_e2e.md)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 TAG, PROBE_N = 'e2e', 4096
 
 
