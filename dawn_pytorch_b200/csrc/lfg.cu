@@ -315,8 +315,11 @@ int decode_core(dawn_lfg* h, float* prediction, float* deformed, cudaStream_t st
 
 extern "C" {
 
+int dawn_check_single_device(void);          // unet.cu: one GPU per process
+
 int dawn_lfg_create(const dawn_lfg_cfg* cfg, dawn_lfg** out) {
   LFG_CHECK(cfg && out, "null argument");
+  LFG_TRY(dawn_check_single_device());
   LFG_CHECK(cfg->num_channels == 3, "lfg: num_channels must be 3");
   LFG_CHECK(cfg->block_expansion % 64 == 0 && cfg->block_expansion <= 128, "lfg: block_expansion must be 64 or 128");
   LFG_CHECK(cfg->num_down_blocks >= 1 && cfg->num_down_blocks <= 4, "lfg: num_down_blocks out of range");

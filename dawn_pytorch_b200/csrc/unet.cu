@@ -1039,8 +1039,25 @@ extern "C" {
 const char* dawn_last_error(void) { return g_last_error.c_str(); }
 const char* dawn_build_info(void) { return "dawn_unet sm_100a; contractions: tcgen05 kind::f16 FP16x3 (TMEM accumulators) + mma.sync m16n8k16 FP16x3 fused attention kernels; fallback mma.sync 3xTF32"; }
 
+// The kernel launchers cache per-function attributes (dynamic shared-memory opt-in, SM count) in process-wide statics: the
+// library is built for ONE GPU PER PROCESS (torchrun / one rank per GPU).  A second device in the same process would launch
+// with attributes that were never set there, so refuse it loudly instead.
+int dawn_check_single_device(void) {
+  static int first_dev = -1;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }     // no driver / no device here (CPU-only build check)
+  if (first_dev < 0) first_dev = dev;
+  if (dev != first_dev) {
+    set_last_error("this process already uses CUDA device " + std::to_string(first_dev) + "; the library supports one GPU per process "
+                   "(launch one rank per GPU), got device " + std::to_string(dev));
+    return -1;
+  }
+  return 0;
+}
+
 int dawn_unet_create(const dawn_unet_cfg* cfg, dawn_unet** out) {
   DAWN_CHECK(cfg && out, "null argument");
+  DAWN_TRY(dawn_check_single_device());
   DAWN_CHECK(cfg->attn_heads == 8 && cfg->attn_dim_head == 32, "only attn_heads=8, attn_dim_head=32 are supported");
   DAWN_CHECK(cfg->resnet_groups == 8, "only resnet_groups=8 is supported");
   DAWN_CHECK(cfg->dim % 64 == 0 && cfg->dim <= 128, "dim must be 64 or 128");
