@@ -10,7 +10,7 @@ timeout 200 python tools/bench_clip.py --clips 2 --graph > $D/bench_clip_graph.l
 for K in tc_conv3_kernel temporal_fused_kernel; do
   timeout 240 ncu --set full --clock-control none --import-source on -k regex:$K -c 1 -f -o $D/$K python tools/profile_step.py 1 > $D/$K.out 2>&1
   ncu -i $D/$K.ncu-rep --page raw --csv > $D/${K}_raw.csv 2>/dev/null
-  ncu -i $D/$K.ncu-rep --page source --csv > $D/${K}_source.csv 2>/dev/null
+  ncu -i $D/$K.ncu-rep --page source --print-source cuda,sass --csv > $D/${K}_source.csv 2>/dev/null
   rm -f $D/$K.ncu-rep
 done
 python tools/show_bench.py $D/bench_default.json | head -16; python tools/show_bench.py $D/bench_bst7.json | head -16

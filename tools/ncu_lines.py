@@ -1,4 +1,5 @@
-"""Aggregate ncu warp-stall samples per CUDA source line: python tools/ncu_lines.py report.ncu-rep source.cu [top]"""
+"""Aggregate ncu warp-stall samples per CUDA source line: python tools/ncu_lines.py report.ncu-rep|export.csv source.cu [top]
+(the .csv form is `ncu -i report.ncu-rep --page source --print-source cuda,sass --csv` exported on the GPU box)"""
 import collections
 import re
 import subprocess
@@ -6,7 +7,10 @@ import sys
 
 rep, srcf = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):
+    out = open(rep).read()
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 src = open(srcf).read().splitlines()
 agg, ins = collections.Counter(), collections.Counter()
 sass = re.compile(r'^"","","(0x[0-9a-f]+)","([^"]*)","(\d+)","(\d+)","(\d+)","(\d+)"')
