@@ -80,3 +80,82 @@ def test_batchnorm_after_conv_folds_into_the_conv():
     t = beta - rm * s
     out = F.conv2d(x, w * s.view(-1, 1, 1, 1), b * s + t, padding=1)
     assert (out - ref).abs().max().item() < 1e-4
+
+
+def test_two_key_cross_attention_is_affine_in_one_gate_per_head_with_gram_layernorm():
+    """The rewrite behind csrc/kernels.cu::ca_tables_* + ca_fused.cu (reference CrossAttention U:481-559): with exactly two keys
+    (null, real) the softmax is one sigmoid gate per head, to_out(o) = u0 + sum_h gate_h * u_h with per-FRAME vectors u, and the
+    output LayerNorm's variance is a 9x9 quadratic form in c = [1, gates] over the centred vectors' Gram matrix."""
+    from oracle import unet_oracle as O
+    g = torch.Generator().manual_seed(4)
+    Fr, n, ci, co, H, D = 3, 11, 64, 128, 8, 8
+    p = "ca"
+    sd = {p + '.norm.g': 1 + 0.2 * torch.randn(ci, generator=g), p + '.to_q.weight': torch.randn(64, ci, generator=g) / 8,
+          p + '.to_kv.weight': torch.randn(128, 2 * co, generator=g) / 16, p + '.null_kv': torch.randn(2, D, generator=g),
+          p + '.q_scale': 1 + 0.2 * torch.randn(D, generator=g), p + '.k_scale': 1 + 0.2 * torch.randn(D, generator=g),
+          p + '.to_out.0.weight': torch.randn(co, 64, generator=g) / 8, p + '.to_out.1.g': 1 + 0.2 * torch.randn(co, generator=g)}
+    tok = torch.randn(Fr, n, ci, generator=g)
+    ctx = torch.randn(Fr, 2 * co, generator=g)
+    ref = O.cross_attention(sd, p, tok, ctx)
+    # --- rewritten form
+    x = O.token_layernorm(tok, sd[p + '.norm.g'])
+    q = (x @ sd[p + '.to_q.weight'].t()).reshape(Fr, n, H, D)
+    kv = ctx @ sd[p + '.to_kv.weight'].t()
+    k, v = kv[:, :64].reshape(Fr, H, D), kv[:, 64:].reshape(Fr, H, D)
+    nk, nv = sd[p + '.null_kv'][0], sd[p + '.null_kv'][1]
+    qs, ks = sd[p + '.q_scale'], sd[p + '.k_scale']
+    kq = F.normalize(k, dim=-1) * ks * qs                                  # per-frame key with both scales folded  (Fr, H, D)
+    nkq = F.normalize(nk, dim=-1) * ks * qs                                # (D,)
+    qn = F.normalize(q, dim=-1)
+    s_real = 8.0 * torch.einsum('fnhd,fhd->fnh', qn, kq)
+    s_null = 8.0 * torch.einsum('fnhd,d->fnh', qn, nkq)
+    gate = torch.sigmoid(s_real - s_null)                                  # softmax over {null, real} -> weight of the real key
+    Wout = sd[p + '.to_out.0.weight']                                      # (co, 64)
+    u0 = Wout @ nv.repeat(H)                                               # (co,)
+    uh = torch.einsum('chd,fhd->fhc', Wout.reshape(co, H, D), v - nv)      # (Fr, H, co)
+    u = torch.cat([u0.expand(Fr, 1, co), uh], dim=1)                       # (Fr, 9, co)
+    uc = u - u.mean(dim=-1, keepdim=True)                                  # centred over channels
+    G = torch.einsum('fac,fbc->fab', uc, uc) / co                          # Gram (Fr, 9, 9)
+    c = torch.cat([torch.ones(Fr, n, 1), gate], dim=-1)                    # (Fr, n, 9)
+    var = torch.einsum('fna,fab,fnb->fn', c, G, c)
+    out = torch.einsum('fna,fac->fnc', c, uc) * torch.rsqrt(var + 1e-5).unsqueeze(-1) * sd[p + '.to_out.1.g']
+    assert (out - ref).abs().max().item() < 2e-4
+
+
+def test_layernorm_folds_into_the_following_projection():
+    """csrc/unet.cu::pack_linear + the QKV epilogues: W(gamma * (x - mu) * rstd) == rstd * (W' x - mu * rowsum(W')), W' = W diag(gamma)
+    (channel LayerNorm without bias, reference U:179-188, 205-213)."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(37, 64, generator=g) * 3 + 1
+    gamma = 1 + 0.2 * torch.randn(64, generator=g)
+    Wm = torch.randn(96, 64, generator=g) / 8
+    mu = x.mean(-1, keepdim=True)
+    rstd = (x.var(-1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
+    ref = ((x - mu) * rstd * gamma) @ Wm.t()
+    Wp = Wm * gamma
+    out = rstd * (x @ Wp.t() - mu * Wp.sum(-1))
+    assert (out - ref).abs().max().item() < 1e-4
+
+
+def test_spatial_linear_attention_context_composes_with_the_out_projection():
+    """csrc/sla_fused.cu::sla_merge_kernel: out = to_out(context^T q) == (Wout . blockdiag(context^T)) q + b, one 256 x C matrix
+    per frame, so q never needs a separate context product (reference SpatialLinearAttention U:602-627)."""
+    from oracle import unet_oracle as O
+    g = torch.Generator().manual_seed(6)
+    C, H, W_, heads, d = 64, 6, 5, 8, 32
+    p = "sla"
+    sd = {p + '.norm.gamma': (1 + 0.2 * torch.randn(C, generator=g)).view(1, C, 1, 1, 1),
+          p + '.fn.to_qkv.weight': torch.randn(768, C, 1, 1, generator=g) / 8,
+          p + '.fn.to_out.weight': torch.randn(C, 256, 1, 1, generator=g) / 16, p + '.fn.to_out.bias': torch.randn(C, generator=g) * 0.05}
+    x = torch.randn(2, C, H, W_, generator=g)
+    ref = O.spatial_linear_attention(sd, p, x)                             # x + to_out(...)
+    xn = O.chan_layernorm(x, sd[p + '.norm.gamma'].view(1, C, 1, 1))
+    qkv = F.conv2d(xn, sd[p + '.fn.to_qkv.weight'])
+    q, k, v = [t.reshape(2, heads, d, H * W_) for t in qkv.chunk(3, dim=1)]
+    q = q.softmax(dim=-2) * d ** -0.5
+    k = k.softmax(dim=-1)
+    ctx = torch.einsum('bhdn,bhen->bhde', k, v)                            # (b, heads, d, e)
+    Wout = sd[p + '.fn.to_out.weight'].view(C, heads, d)                   # columns = (head, e)
+    Mf = torch.einsum('che,bhde->bchd', Wout, ctx).reshape(2, C, heads * d)    # per-frame composed matrix (C x 256) acting on q
+    out = torch.einsum('bck,bkn->bcn', Mf, q.reshape(2, heads * d, H * W_)) + sd[p + '.fn.to_out.bias'].view(1, C, 1)
+    assert (x + out.reshape(2, C, H, W_) - ref).abs().max().item() < 1e-4
