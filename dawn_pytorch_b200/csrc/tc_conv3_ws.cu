@@ -1,16 +1,13 @@
-// tcgen05 3x3 convolution with a shared-memory HALO tile (sm_100a) — the Block.proj of the reference (U:229, 234).
-//
-// tc_gemm.cu treats a 3x3 conv as 9 independent K panels per 64 channels: the same activations are gathered, split to
-// fp16 hi/lo and stored 9 times.  Here a CTA stages the (16+2) x (8+2) pixel halo of its 16x8-pixel output tile ONCE per
-// 64-channel chunk (6.3x less gather/convert/store work) and the 9 taps are 9 shifted operand windows over that tile:
-// measured on B200, with descriptor base_offset = 0 the UMMA 128-byte swizzle follows ABSOLUTE shared-memory address bits,
-// so a K-major operand may start at any 128-byte row and use any row-multiple stride between its 8-row groups:
-//     window(dy,dx): start = halo + ((dy+1)*10 + (dx+1))*128 B,  stride between 8-pixel rows (SBO) = 10*128 B.
-// Everything else follows tc_gemm.cu: FP16x3 split precision, TMEM double-buffered accumulators drained into RN fp32
-// registers (once per 64-channel chunk = 108 MMAs), persistent warp-specialised CTA (8 producer warps, 4/8 epilogue warps,
-// MMA issuer, weight loader), row-per-thread epilogue with bias + GroupNorm partial statistics.
+// EXPERIMENT (off by default, DAWN_CONV3_WSTAT=1): weight-stationary variant of tc_conv3.cu for the dim -> dim (64 -> 64) convs.
+// In tc_conv3.cu every 128-pixel tile re-streams its nine (hi | lo) weight panels from L2 (147 KB per tile against 46 KB of
+// activations) through a 4-stage ring; ncu (snapshot K) shows the tensor pipe busy for ~4.0k of ~13.4k cycles per tile.  For
+// Cin = Cout = 64 the whole weight set is 147 KB and fits in shared memory next to ONE activation stage (46 KB) and the epilogue
+// staging (205 KB in total): the loader fills it once per persistent CTA and the MMA issuer never waits for weights again.  The
+// activation stage is single-buffered, but the producers already hold the next tile's pixels in registers while they wait for the
+// slot, so only their convert + store (~0.7k cycles) is exposed between two tiles' MMAs (~5k cycles).
+// Mechanical derivative of tc_conv3.cu (kernel renamed; A_STAGES 2 -> 1, B ring -> 9 resident panels, loader and issuer loops
+// adjusted); the validated kernel is untouched.  Fold back once measured.
 #include <cuda_fp16.h>
-#include <cstdlib>
 #include "common.cuh"
 #include "gemm.cuh"
 #include "tc_common.cuh"
@@ -28,11 +25,11 @@ constexpr int A_HALO = 23 * 1024;              // 180 * 128 = 23040 B, padded to
 constexpr int NPROD = 256;
 
 template <int BN>
-struct CCfg {
+struct CCfgWS {
   static constexpr int NWG = BN / 64;
   static constexpr int B_PANEL = BN * 128;                     // one (tap, chunk) weight panel, hi or lo
-  static constexpr int A_STAGES = 2;
-  static constexpr int B_STAGES = (BN == 64) ? 4 : 3;
+  static constexpr int A_STAGES = 1;                           // weight-stationary variant: the room goes to the 9 resident panels
+  static constexpr int B_STAGES = 9;                           // one RESIDENT (hi | lo) panel per tap, loaded once per CTA (Cin = 64 only)
   static constexpr int A_BYTES = A_STAGES * 2 * A_HALO;        // hi + lo
   static constexpr int B_BYTES = B_STAGES * 2 * B_PANEL;
   static constexpr int EPI_STAGE = NWG * 4 * 32 * 20 * 4;
@@ -47,9 +44,9 @@ struct CCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const GemmParams p, const float* __restrict__ Bimg,
+__global__ void __launch_bounds__(CCfgWS<BN>::NTHREADS, 1) tc_conv3_ws_kernel(const GemmParams p, const float* __restrict__ Bimg,
                                                                           int tiles_y, int tiles_x, int tiles_n) {
-  using C = CCfg<BN>;
+  using C = CCfgWS<BN>;
   constexpr int B_PANEL = C::B_PANEL, A_STAGES = C::A_STAGES, B_STAGES = C::B_STAGES, NWG = C::NWG;
   constexpr int MMA_WARP = C::MMA_WARP, LOAD_WARP = C::LOAD_WARP, TMEM_COLS = C::TMEM_COLS, ACC_COLS = C::ACC_COLS;
   extern __shared__ uint8_t smem_raw[];
@@ -141,23 +138,12 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
       }
     }
   } else if (warp == LOAD_WARP) {
-    // =============================================================== weight loader: one (tap, chunk) panel pair per slot
+    // =============================================================== weight loader: all 9 tap panels, ONCE per CTA (Cin = 64, one n-tile)
     if (lane == 0) {
-      uint32_t bit = 0;
-      const int KC = 9 * NCH;                                  // panels per n-tile in the weight image: kc = tap*NCH + cc
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int f, y0, x0, nt;
-        decode(tile, f, y0, x0, nt);
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(Bimg) + (size_t)nt * KC * (2 * B_PANEL);
-        for (int cc = 0; cc < NCH; ++cc)
-          for (int tap = 0; tap < 9; ++tap, ++bit) {
-            const int s = bit % B_STAGES;
-            const uint32_t round = bit / B_STAGES;
-            mbar_wait(&b_free[s], (round & 1) ^ 1);
-            mbar_arrive_expect_tx(&b_full[s], 2 * B_PANEL);
-            bulk_copy_g2s(smemB + s * 2 * B_PANEL, src + (size_t)(tap * NCH + cc) * (2 * B_PANEL), 2 * B_PANEL, &b_full[s]);
-          }
-      }
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(Bimg);
+      mbar_arrive_expect_tx(&b_full[0], 9 * 2 * B_PANEL);
+      for (int tap = 0; tap < 9; ++tap)
+        bulk_copy_g2s(smemB + tap * 2 * B_PANEL, src + (size_t)tap * (2 * B_PANEL), 2 * B_PANEL, &b_full[0]);
     }
   } else if (warp == MMA_WARP) {
     // =============================================================== MMA issuer
@@ -165,7 +151,9 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
       const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t idesc2 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       constexpr uint64_t SBO_HALO = (uint64_t)(HW * 128 / 16);   // 10 pixel rows of 128 B between 8-row groups
-      uint32_t ait = 0, bit = 0, cg = 0;
+      uint32_t ait = 0, cg = 0;
+      mbar_wait(&b_full[0], 0);                                // the resident weight panels have landed
+      tc_fence_after();
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         for (int cc = 0; cc < NCH; ++cc, ++ait, ++cg) {
           const int sa = ait % A_STAGES;
@@ -176,10 +164,8 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smemA + sa * 2 * A_HALO), a_lo = a_hi + A_HALO;
           const uint32_t d = tmem_base + buf * ACC_COLS;
-          for (int tap = 0; tap < 9; ++tap, ++bit) {
-            const int sb = bit % B_STAGES;
-            mbar_wait(&b_full[sb], (bit / B_STAGES) & 1);
-            tc_fence_after();
+          for (int tap = 0; tap < 9; ++tap) {
+            const int sb = tap;
             const int ky = tap / 3, kx = tap - ky * 3;          // window start: halo pixel (ky, kx)
             const uint32_t woff = (uint32_t)((ky * HW + kx) * 128);
             // K-major SW128 descriptors: start address, LBO = 1 (unused), SBO, version 1, layout SWIZZLE_128B, base_offset 0
@@ -200,7 +186,6 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
                 tc_mma_f16(d, ahi + o, bhi + o, idesc, 1u);
               }
             }
-            tc_commit(&b_free[sb]);
           }
           tc_commit(&a_free[sa]);
           tc_commit(&acc_full[buf]);
@@ -300,12 +285,12 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
 }
 
 template <int BN>
-int launch_c3(const GemmParams& p, const float* Bimg, cudaStream_t st) {
-  using C = CCfg<BN>;
+int launch_c3_ws(const GemmParams& p, const float* Bimg, cudaStream_t st) {
+  using C = CCfgWS<BN>;
   static bool attr_set = false;
   static int num_sms = 0;
   if (!attr_set) {
-    DAWN_CUDA_OK(cudaFuncSetAttribute(tc_conv3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_DYN));
+    DAWN_CUDA_OK(cudaFuncSetAttribute(tc_conv3_ws_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_DYN));
     int dev = 0;
     DAWN_CUDA_OK(cudaGetDevice(&dev));
     DAWN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -314,38 +299,15 @@ int launch_c3(const GemmParams& p, const float* Bimg, cudaStream_t st) {
   const int tiles_y = p.IH / TH, tiles_x = p.IW / TW, tiles_n = p.N / BN;
   const int F = p.M / (p.IH * p.IW);
   const int grid = std::min(F * tiles_y * tiles_x * tiles_n, num_sms);
-  tc_conv3_kernel<BN><<<grid, C::NTHREADS, C::SMEM_DYN, st>>>(p, Bimg, tiles_y, tiles_x, tiles_n);
+  tc_conv3_ws_kernel<BN><<<grid, C::NTHREADS, C::SMEM_DYN, st>>>(p, Bimg, tiles_y, tiles_x, tiles_n);
   DAWN_LAUNCH_OK();
   return 0;
 }
 
 }  // namespace
 
-// 3x3, stride 1, same padding, static weights, spatial size a multiple of the 16x8 tile, 64-channel chunks, EPI_PLAIN without residual
-bool tc_conv3_supported(const GemmParams& p, int epi) {
-  if (epi != EPI_PLAIN || p.Res != nullptr || p.perm_in || p.perm_out) return false;
-  if (p.ntaps != 9 || p.in_stride != 1 || p.out_stride != 1 || p.oy0 != 0 || p.ox0 != 0) return false;
-  if (p.IH != p.OH || p.IW != p.OW || p.OHs != p.OH || p.OWs != p.OW) return false;
-  if (p.IH % TH != 0 || p.IW % TW != 0) return false;
-  if (p.Cin % 64 != 0 || p.N % 64 != 0 || p.K != 9 * p.Cin) return false;
-  if (p.b_batch_stride != 0 || p.rows_per_batch != p.M) return false;
-  if ((p.lda & 3) || (p.ldo & 3)) return false;
-  if (p.stats && (p.cpg % 8 != 0)) return false;
-  if (p.up2 && (p.stats != nullptr || p.N != 256)) return false;
-  return true;
-}
-
-int launch_tc_conv3_bst7(const GemmParams& p, const float* Bimg, cudaStream_t st);   // tc_conv3_exp.cu (experiment, off by default)
-bool tc_conv3_ws_supported(const GemmParams& p);                                       // tc_conv3_ws.cu (experiment, off by default)
-int launch_tc_conv3_ws(const GemmParams& p, const float* Bimg, cudaStream_t st);
-
-int launch_tc_conv3(const GemmParams& p, const float* Bimg, cudaStream_t st) {
-  if (!tc_conv3_supported(p, EPI_PLAIN)) { set_last_error("launch_tc_conv3: unsupported geometry"); return -1; }
-  static const bool bst7 = [] { const char* e = getenv("DAWN_CONV3_BSTAGES"); return e && e[0] == '7'; }();
-  static const bool wstat = [] { const char* e = getenv("DAWN_CONV3_WSTAT"); return e && e[0] == '1'; }();
-  if (wstat && tc_conv3_ws_supported(p)) return launch_tc_conv3_ws(p, Bimg, st);
-  if (tc_tile_n(p.N) == 128) return launch_c3<128>(p, Bimg, st);
-  return bst7 ? launch_tc_conv3_bst7(p, Bimg, st) : launch_c3<64>(p, Bimg, st);
-}
+// Cin = Cout = 64, one n-tile, no up2 epilogue; everything else as tc_conv3_supported (checked by the caller)
+bool tc_conv3_ws_supported(const GemmParams& p) { return p.Cin == 64 && p.N == 64 && !p.up2; }
+int launch_tc_conv3_ws(const GemmParams& p, const float* Bimg, cudaStream_t st) { return launch_c3_ws<64>(p, Bimg, st); }
 
 }  // namespace dawn
