@@ -100,9 +100,6 @@ class GaussianDiffusion(nn.Module):
         Frame-sharded UNet (`unet.init_shard`): `shape`, `cond` and the returned sample hold this rank's frames; the
         dynamic-threshold quantile is selected over the whole clip (all-reduced radix select) and the default noise is
         the rank's slice of ONE clip-wide stream (same `seed` on every rank; drawn on rank 0 and broadcast if None)."""
-        if cond_scale != 1:
-            raise NotImplementedError("cond_scale != 1 goes through DynamicNfUnet3D.forward_with_cond_scale (two forwards); "
-                                      "the fused sampler implements DAWN's shipped cond_scale = 1.0")
         device = self.betas.device
         b, ch, Fr, h, w = shape
         unet = self.denoise_fn
@@ -112,17 +109,33 @@ class GaussianDiffusion(nn.Module):
         n = ch * Fr * h * w
         q = float(self.dynamic_thres_percentile) if (clip_denoised and self.use_dynamic_thres) else 0.0
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        guided = cond_scale != 1 and getattr(unet, "has_cond", True)
         if use_graph:
+            if guided:
+                raise NotImplementedError("use_graph captures the cond_scale = 1 loop (DAWN's shipped setting); "
+                                          "classifier-free guidance runs eagerly")
             return self._ddim_sample_graph(unet, fea, cond, img, pairs, draw, q, st)
         scratch = torch.empty(n + 512, dtype=torch.int32, device=device)
         eps = torch.empty((ch, Fr, h, w), device=device)
+        eps_null = torch.empty_like(eps) if guided else None
         for i in range(b):
             unet.update_num_frames(Fr)
-            unet.set_clip_invariants(fea[i], cond[i])
+            if not guided:
+                unet.set_clip_invariants(fea[i], cond[i])
             x = img[i]
             for k, (t, t_next) in enumerate(pairs):
                 t_dev = torch.full((1,), t, device=device, dtype=torch.long)
-                unet.forward_x3(x, t_dev, eps)
+                if guided:
+                    # classifier-free guidance (reference forward_with_cond_scale U:879-890 inside ddim_sample U:1176-1180):
+                    # eps = eps_null + (eps_cond - eps_null) * cond_scale, the null condition being all zeros (learn_null_cond=False,
+                    # U:920).  Two hoisted forwards per step, each after rebuilding the per-clip conditioning tables (~0.5 ms).
+                    unet.set_clip_invariants(fea[i], cond[i])
+                    unet.forward_x3(x, t_dev, eps)
+                    unet.set_clip_invariants(fea[i], torch.zeros_like(cond[i]))
+                    unet.forward_x3(x, t_dev, eps_null)
+                    torch.add(eps_null, eps - eps_null, alpha=float(cond_scale), out=eps)
+                else:
+                    unet.forward_x3(x, t_dev, eps)
                 ca, cb, san, c, sigma = self.ddim_coefficients(t, t_next)
                 noise = draw(k, (ch, Fr, h, w)).to(device).contiguous() if t_next > 0 else None
                 check(lib.dawn_unet_ddim_step(unet._handle, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(eps.data_ptr()),

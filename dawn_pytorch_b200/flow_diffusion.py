@@ -131,8 +131,6 @@ class FlowDiffusion(nn.Module):
             ref_pose = torch.cat([ref_pose, init_pose[:, :, -1].unsqueeze(-1)], dim=-1)
         ref_text = torch.cat([sample_audio_hubert, ref_pose - init_pose, ref_eye - init_eye], dim=-1)          # FD:350
         b = fea.shape[0]
-        if cond_scale != 1:
-            raise NotImplementedError("sample_one_video implements DAWN's shipped cond_scale = 1.0 (config/DAWN_128.yaml:8)")
         fea272 = torch.cat([fea, bbox_mask], dim=1)                                     # GaussianDiffusion.sample, U:1151
         h, w = fea272.shape[-2:]
         pred = self.diffusion.ddim_sample(fea272, (b, self.diffusion.channels, self.diffusion.num_frames, h, w), cond=ref_text,

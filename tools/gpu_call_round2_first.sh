@@ -7,6 +7,7 @@ DAWN_CONV3_BSTAGES=7 timeout 300 python bench.py --no-cpu-baseline > $D/bench_bs
 DAWN_CONV3_BSTAGES=7 timeout 300 python -m pytest tests/test_unet_gpu.py -q -k "golden or submodule or cfg2" > $D/pytest_bst7.log 2>&1
 DAWN_CONV3_WSTAT=1 timeout 300 python bench.py --no-cpu-baseline > $D/bench_wstat.json 2> $D/bench_wstat.err
 DAWN_CONV3_WSTAT=1 timeout 300 python -m pytest tests/test_unet_gpu.py -q -k "golden or submodule or cfg2" > $D/pytest_wstat.log 2>&1
+timeout 200 python -m pytest tests -m staged_gpu -q -s > $D/pytest_staged.log 2>&1
 timeout 200 python tools/bench_clip.py --clips 2 > $D/bench_clip.log 2>&1
 timeout 200 python tools/bench_clip.py --clips 2 --graph > $D/bench_clip_graph.log 2>&1
 for K in tc_conv3_kernel temporal_fused_kernel; do
@@ -16,4 +17,4 @@ for K in tc_conv3_kernel temporal_fused_kernel; do
   rm -f $D/$K.ncu-rep
 done
 python tools/show_bench.py $D/bench_default.json | head -16; python tools/show_bench.py $D/bench_bst7.json | head -16; python tools/show_bench.py $D/bench_wstat.json | head -16; tail -3 $D/pytest_wstat.log
-tail -3 $D/pytest_bst7.log; tail -2 $D/bench_clip.log; tail -2 $D/bench_clip_graph.log; du -sh gpurun_out
+tail -3 $D/pytest_bst7.log; tail -3 $D/pytest_staged.log; tail -2 $D/bench_clip.log; tail -2 $D/bench_clip_graph.log; du -sh gpurun_out
