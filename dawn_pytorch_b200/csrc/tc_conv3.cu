@@ -335,17 +335,10 @@ bool tc_conv3_supported(const GemmParams& p, int epi) {
   return true;
 }
 
-int launch_tc_conv3_bst7(const GemmParams& p, const float* Bimg, cudaStream_t st);   // tc_conv3_exp.cu (experiment, off by default)
-bool tc_conv3_ws_supported(const GemmParams& p);                                       // tc_conv3_ws.cu (experiment, off by default)
-int launch_tc_conv3_ws(const GemmParams& p, const float* Bimg, cudaStream_t st);
-
 int launch_tc_conv3(const GemmParams& p, const float* Bimg, cudaStream_t st) {
   if (!tc_conv3_supported(p, EPI_PLAIN)) { set_last_error("launch_tc_conv3: unsupported geometry"); return -1; }
-  static const bool bst7 = [] { const char* e = getenv("DAWN_CONV3_BSTAGES"); return e && e[0] == '7'; }();
-  static const bool wstat = [] { const char* e = getenv("DAWN_CONV3_WSTAT"); return e && e[0] == '1'; }();
-  if (wstat && tc_conv3_ws_supported(p)) return launch_tc_conv3_ws(p, Bimg, st);
   if (tc_tile_n(p.N) == 128) return launch_c3<128>(p, Bimg, st);
-  return bst7 ? launch_tc_conv3_bst7(p, Bimg, st) : launch_c3<64>(p, Bimg, st);
+  return launch_c3<64>(p, Bimg, st);
 }
 
 }  // namespace dawn

@@ -88,6 +88,12 @@ def synth_state_dict(schema):
     return {n: torch.from_numpy(np.ascontiguousarray(synth_value(n, s))).float() for n, s in schema}
 
 
+def probe_indices(name: str, numel: int, n: int) -> np.ndarray:
+    """n fixed element indices into a flat tensor of `numel` elements (golden probes; exact on every platform)."""
+    u = uniform01('probe/' + name, n)
+    return np.minimum((u.astype(np.float64) * numel).astype(np.int64), numel - 1)
+
+
 def synth_inputs(tag: str, F: int, h: int, w: int, cond_dim: int = 1032, fea_ch: int = 272):
     """Synthetic clip: x_t ~ N(0,1) (3,F,h,w); fea >= 0 (post-ReLU features, LFG/modules/util.py:127-132,
     FD:45-50) (fea_ch,h,w); cond ~ N(0,1) (F,cond_dim).  Returned as torch tensors with batch dim."""

@@ -10,18 +10,6 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "staged_gpu: GPU parity tests awaiting their first B200 validation (run with -m staged_gpu; "
-                                       "skipped without a CUDA device, not part of -m gpu)")
-
-
-def pytest_collection_modifyitems(config, items):
-    import torch
-    if torch.cuda.is_available():
-        return
-    skip = pytest.mark.skip(reason="needs a CUDA device")
-    for item in items:
-        if "staged_gpu" in item.keywords:
-            item.add_marker(skip)
 
 
 @pytest.fixture(scope="session")

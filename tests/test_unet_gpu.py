@@ -1,6 +1,8 @@
 """-m gpu: parity of the CUDA path (through the reference-facing module API -> C-ABI) against
 (1) golden vectors produced by the REAL reference, (2) the CPU oracle on the same seeded inputs,
 (3) size-independent properties at sizes the oracle cannot reach in seconds."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -137,6 +139,63 @@ def test_full_size_properties_cfg3():
     d_near = (c[:, 0] - a[:, 0]).abs().max().item()
     d_far = (c[:, 199] - a[:, 199]).abs().max().item()
     assert d_near > 1e-2 and d_far < d_near
+
+
+def test_cfg3_matches_reference_golden_probes():
+    """BASELINE configs[2] (the benchmarked shape: 200 f x 64x64, window active) against the REAL reference
+    (oracle/make_golden_cfg3.py: eps on a stride-4 lattice + 65536 eps probes + 4096 probes and abs-mean at each of the 46
+    sub-module boundaries).  Exercises the level-0 paths that only exist at full size (persistent halo conv over 148 CTAs,
+    4096-pixel temporal attention, spatial-linear-attention splits) through BOTH entries: forward_with_cond_scale(x275) with
+    taps, and the hoisted forward_x3."""
+    CASE, FR, H, WD, T, SUB = "cfg3", 200, 64, 64, 500, 4
+
+    def probe_idx(name, numel, n=4096):
+        return W.probe_indices(name, numel, n)
+
+    g = np.load(os.path.join(G.ROOT, "tests", "golden", "cfg3.npz"))
+    net = G.cuda_net()
+    x_t, fea, cond = W.synth_inputs(CASE, FR, H, WD)
+    t = torch.full((1,), T, dtype=torch.long).cuda()
+    names = sorted(k.split("/")[1] for k in g.files if k.startswith("tap/") and k.endswith("/vals"))
+    assert len(names) >= 40
+    x = torch.cat([x_t, fea.unsqueeze(2).expand(-1, -1, FR, -1, -1)], dim=1).contiguous().cuda()
+    bufs = net.request_taps(names, FR, H, WD, torch.device("cuda"))
+    try:
+        net.update_num_frames(FR)
+        with torch.no_grad():
+            out = net.forward_with_cond_scale(x, t, cond=cond.cuda(), cond_scale=1.0)
+        torch.cuda.synchronize()
+        worst = {}
+        for n in names:
+            flat = bufs[n].reshape(-1)
+            assert list(bufs[n].shape) == g[f"tap/{n}/shape"].tolist(), n
+            idx = torch.from_numpy(probe_idx(f"{CASE}/{n}", flat.numel())).cuda()
+            got = flat[idx].cpu()
+            worst[n] = G.over_tol(got, torch.from_numpy(g[f"tap/{n}/vals"]))
+            am = flat.double().abs().mean().item()
+            assert abs(am - float(g[f"tap/{n}/absmean"])) <= 1e-3 * float(g[f"tap/{n}/absmean"]) + 1e-6, (n, am)
+    finally:
+        net.clear_taps()
+    del x, bufs
+    print("cfg3 worst taps:", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
+    bad = {k: v for k, v in worst.items() if v > 1.0}
+    assert not bad, bad
+
+    def check_eps(o, tag):
+        o = o.cpu()
+        r_sub = G.over_tol(o[0][:, :, ::SUB, ::SUB], torch.from_numpy(g["eps_sub"]))
+        idx = torch.from_numpy(probe_idx(f"{CASE}/eps", o.numel(), 65536))
+        r_pr = G.over_tol(o.reshape(-1)[idx], torch.from_numpy(g["eps_probe"]))
+        am, sm = o.double().abs().mean().item(), o.double().sum().item()
+        print(f"cfg3 {tag}: eps lattice {r_sub:.3f} x tol, probes {r_pr:.3f} x tol, absmean {am:.6f} (ref {g['eps_stats'][0]:.6f})")
+        assert r_sub <= 1.0 and r_pr <= 1.0
+        assert abs(am - g["eps_stats"][0]) <= 1e-4 and abs(sm - g["eps_stats"][1]) <= 1e-4 * o.numel() ** 0.5 + 1e-3 * abs(g["eps_stats"][1])
+
+    check_eps(out, "general entry")
+    net.set_clip_invariants(fea[0].cuda(), cond[0].cuda())
+    o3 = net.forward_x3(x_t[0].cuda(), t)
+    torch.cuda.synchronize()
+    check_eps(o3[None], "hoisted entry")
 
 
 def test_ddim_sampler_steps_match_reference_golden():
@@ -306,3 +365,26 @@ def test_other_window_width_against_oracle():
         ref40 = O.unet_forward(G.synth_sd(), O.UnetCfg(), x, t, cond)
     assert G.over_tol(out, ref) <= 1.0
     assert (ref - ref40).abs().max().item() > 1e-3          # the window really matters on this clip
+
+
+def test_classifier_free_guidance_sampling_matches_reference_golden():
+    """N4: `ddim_sample(cond_scale=2)` — two hoisted UNet forwards per step (conditioning / all-zero null conditioning, U:879-890,
+    920) — against the REAL reference's ddim_sample on the 'odd' clip (oracle/make_golden_cfg.py, 3 steps, injected noise)."""
+    from dawn_pytorch_b200 import DynamicNfGaussianDiffusion
+    g = np.load(os.path.join(G.ROOT, "tests", "golden", "ddim_cfg2_odd.npz"))
+    steps, scale = int(g["steps"]), float(g["cond_scale"])
+    net = G.cuda_net()
+    D = DynamicNfGaussianDiffusion(denoise_fn=net, num_frames=40, image_size=32, sampling_timesteps=steps, timesteps=1000,
+                                   loss_type='l2', use_dynamic_thres=True, null_cond_prob=0.1, ddim_sampling_eta=1.0).cuda()
+    F, h, w, _ = G.CASES["odd"]
+    _, fea, cond = W.synth_inputs("odd", F, h, w)
+    D.update_num_frames(F)
+
+    def noise_fn(k, shape):
+        return torch.from_numpy(W.pseudo_normal(f"cfg2/noise{k}", tuple(shape)))
+
+    img = D.ddim_sample(fea.cuda(), (1, 3, F, h, w), cond=cond.cuda(), cond_scale=scale, noise_fn=noise_fn)
+    torch.cuda.synchronize()
+    d = (img.cpu() - torch.from_numpy(g["sample"])).abs().max().item()
+    print(f"cfg sampling (cond_scale {scale}, {steps} steps): max|d| = {d:.3e}")
+    assert d < 2e-4
