@@ -1,0 +1,629 @@
+// Temporal attention of the 64-channel levels on tcgen05 (reference U:648-725 == LA:71-99, 275-342 inside Residual(PreNorm(...)),
+// U:763-765).  One work unit = one pixel's frame window (<= 224 frames) and a query range inside it; a persistent CTA per SM walks
+// the units.  Everything between the layer input and the layer output stays on chip:
+//
+//   x[w0 .. w0+wn, p, :] -> LayerNorm statistics, fp16 hi|lo split -> X (shared, K-major, 128-B swizzle)
+//   per head h (8):   PROJ   [q|k|v]_h = X . W'_h^T            UMMA 128 x 96 x 64 per row tile          (SS, TMEM fp32)
+//                     E1     LN fold, rotary(q, k), split -> Q_h, K_h (rows) and V_h^T (dims x keys) in shared memory
+//                     S      S = Q_h . K_h^T                    UMMA 128 x 160 x 32 per row tile         (SS)
+//                     E2     + relative bias / band mask (table), row softmax with warp-private rows, P = exp2(S - max) written
+//                            back IN PLACE into the S columns as packed fp16 hi | lo
+//                     PV     O = P . V_h                        UMMA 128 x 32 x 160, A operand from TMEM (TS)
+//                     E3     O / rowsum, split -> O_h (shared)
+//                     Y      Y += O_h . Wout_h^T                UMMA 128 x 64 x 32, accumulated over the 8 heads in TMEM
+//   out = residual + Y
+//
+// Every product is the 3-term fp16 split (lo*hi + hi*lo + hi*hi, fp32 accumulate): SURVEY App. D.  The window's rows are cut into two
+// balanced row tiles (each <= 112 rows on TMEM lanes 0..127); compute warpgroup j (4 warps = 128 lanes) owns tile j for the whole unit, so
+// its softmax runs while the other tile's MMAs execute.  Roles: warps 0-7 compute (two warpgroups), warp 8 lane 0 issues every
+// tcgen05.mma, warp 9 lane 0 streams the per-head weight images (cp.async.bulk).  TMEM (512 columns): S/P tiles 2 x 160 (the QKV
+// accumulator aliases their first 96 columns), O 2 x 32, Y 2 x 64.  The sequence length is unbounded: long sequences are cut into
+// segments whose windows overlap by the band (K/V of the overlap are re-projected).
+#include <cuda_fp16.h>
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "temporal_tc.cuh"
+
+namespace dawn {
+namespace {
+
+using namespace tc;
+
+constexpr int WMAX = kTtcWindowMax;
+constexpr int SN = 160;                    // key columns of an S tile
+constexpr int CW = 128;                    // columns one softmax thread looks at (32 rows + 2*band <= 112, + 16 alignment)
+constexpr int NTH = 320;
+constexpr int MMA_WARP = 8, LOAD_WARP = 9;
+constexpr float LOG2E = 1.4426950408889634f;
+
+// shared-memory map (bytes from a 1024-aligned base); every UMMA operand starts on a 1024-byte swizzle atom
+constexpr int XH_OFF = 0;                          // X hi: 224 rows x 128 B
+constexpr int XL_OFF = XH_OFF + WMAX * 128;
+constexpr int WQ_OFF = XL_OFF + WMAX * 128;        // W'_h hi (96 x 128 B) | lo
+constexpr int WO_OFF = WQ_OFF + 2 * 96 * 128;      // Wout_h (64 x 128 B)
+constexpr int K_OFF = WO_OFF + 64 * 128;           // K_h rows: [hi 32 | lo 32] halfs
+constexpr int Q_OFF = K_OFF + WMAX * 128;
+constexpr int O_OFF = Q_OFF + WMAX * 128;
+constexpr int VH_OFF = O_OFF + WMAX * 128;         // V_h^T hi: 4 chunks of 64 keys, each 32 dims x 128 B
+constexpr int VL_OFF = VH_OFF + 4 * 4096;
+constexpr int TBL_OFF = VL_OFF + 4 * 4096;         // per-warpgroup bias/mask table of the current head
+constexpr int ST_OFF = TBL_OFF + 2 * kTtcTable * 4;
+constexpr int WS_OFF = ST_OFF + WMAX * 8;          // wsum[768]
+constexpr int SMEM_END = WS_OFF + 768 * 4;
+constexpr int SMEM_DYN = SMEM_END + 1024;
+constexpr int WQ_BYTES = 2 * 96 * 128, WO_BYTES = 64 * 128;
+
+// TMEM columns
+__device__ __forceinline__ constexpr uint32_t s_col(int j) { return 160u * j; }
+__device__ __forceinline__ constexpr uint32_t o_col(int j) { return 320u + 32u * j; }
+__device__ __forceinline__ constexpr uint32_t y_col(int j) { return 384u + 64u * j; }
+
+constexpr uint32_t idesc_n(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }   // D f32, A/B f16, K-major, M = 128
+
+// D[tmem] (+)= A[tmem, fp16 pairs packed per 32-bit column] * B[smem]
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[64], int o) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[o + 0]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), "r"(r[o + 6]), "r"(r[o + 7]),
+      "r"(r[o + 8]), "r"(r[o + 9]), "r"(r[o + 10]), "r"(r[o + 11]), "r"(r[o + 12]), "r"(r[o + 13]), "r"(r[o + 14]), "r"(r[o + 15]),
+      "r"(r[o + 16]), "r"(r[o + 17]), "r"(r[o + 18]), "r"(r[o + 19]), "r"(r[o + 20]), "r"(r[o + 21]), "r"(r[o + 22]), "r"(r[o + 23]),
+      "r"(r[o + 24]), "r"(r[o + 25]), "r"(r[o + 26]), "r"(r[o + 27]), "r"(r[o + 28]), "r"(r[o + 29]), "r"(r[o + 30]), "r"(r[o + 31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// one element -> fp16 hi / lo bit patterns (same rounding as split_f16x2)
+__device__ __forceinline__ void split_f16(float x, uint16_t& hi, uint16_t& lo) {
+  const float h = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  hi = __half_as_ushort(__float2half_rn(h));
+  lo = __half_as_ushort(__float2half_rn(x - h));
+}
+// 8 consecutive values of a row -> one 16-byte chunk of the hi half and one of the lo half of a [hi 32 | lo 32] operand row
+__device__ __forceinline__ void store_row_chunk(uint8_t* base, int row, int c8, const float (&v)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_f16x2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+  *reinterpret_cast<uint4*>(base + swz(row, c8)) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(base + swz(row, 4 + c8)) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+struct Bars {
+  uint64_t x_ready, wq_ready, wq_free, wo_ready, wo_free, kv_ready;
+  uint64_t proj_ready[2], s_ready[2], p_ready[2], o_ready[2], oh_ready[2], y_ready[2];
+};
+
+__global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ Bars bars;
+  __shared__ uint32_t s_tmem_base;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(&bars.x_ready, 256); mbar_init(&bars.kv_ready, 256);
+    mbar_init(&bars.wq_ready, 1); mbar_init(&bars.wq_free, 1); mbar_init(&bars.wo_ready, 1); mbar_init(&bars.wo_free, 1);
+    for (int j = 0; j < 2; ++j) {
+      mbar_init(&bars.proj_ready[j], 1); mbar_init(&bars.s_ready[j], 1); mbar_init(&bars.o_ready[j], 1); mbar_init(&bars.y_ready[j], 1);
+      mbar_init(&bars.p_ready[j], 128); mbar_init(&bars.oh_ready[j], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  // operand buffers start as zeros: rows beyond a window are multiplied (into masked or unused results) and must be finite
+  {
+    uint4* p0 = reinterpret_cast<uint4*>(smem + XH_OFF);
+    for (int i = tid; i < (2 * WMAX * 128) / 16; i += NTH) p0[i] = make_uint4(0, 0, 0, 0);
+    uint4* p1 = reinterpret_cast<uint4*>(smem + K_OFF);
+    for (int i = tid; i < (TBL_OFF - K_OFF) / 16; i += NTH) p1[i] = make_uint4(0, 0, 0, 0);
+    float* ws = reinterpret_cast<float*>(smem + WS_OFF);
+    for (int i = tid; i < 768; i += NTH) ws[i] = a.wsum[i];
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  const int nunits = a.P * a.nseg;
+  const int band = a.band;
+
+  if (warp < 8) {
+    // ======================================================================= compute warpgroups
+    const int j = warp >> 2;                               // tile owned by this warpgroup
+    const int wq = warp & 3;                               // TMEM lane quarter
+    const int l = wq * 32 + lane;                          // lane = row inside the tile
+    const int wgtid = tid & 127;
+    const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+    float* tb = reinterpret_cast<float*>(smem + TBL_OFF) + j * kTtcTable;
+    const float2* s_stat = reinterpret_cast<const float2*>(smem + ST_OFF);
+    const float* ws = reinterpret_cast<const float*>(smem + WS_OFF);
+    uint32_t it = 0, ui = 0;                               // head iterations / units done by this CTA
+    uint32_t nact[2] = {0, 0}, nq[2] = {0, 0};             // completed phases of the per-tile barriers (rows exist / queries exist)
+
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ui) {
+      const int pix = u / a.nseg;
+      const TtcSegment sg = a.seg[u - pix * a.nseg];
+      TtcTile tl[2];
+      ttc_tiles(sg, band, tl);
+      const bool act[2] = {tl[0].r1 > tl[0].r0, tl[1].r1 > tl[1].r0};
+      const bool hq[2] = {tl[0].q1 > tl[0].q0, tl[1].q1 > tl[1].q0};
+      const TtcTile T = tl[j];
+      const int row = T.r0 + l;                            // window row of this thread
+      const bool row_ok = row < T.r1;
+      const bool dbg = (a.dbg != nullptr) && u == 0;
+
+      // ------------------------------------------------------------------ prologue: x rows -> LN statistics + fp16 split
+      {
+        const int l16 = tid & 15, rg = tid >> 4;           // 16 lanes x float4 = one 64-channel row; 16 rows per pass
+        float2* st = reinterpret_cast<float2*>(smem + ST_OFF);
+#pragma unroll 2
+        for (int r0 = 0; r0 < sg.wn; r0 += 16) {
+          const int r = r0 + rg;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < sg.wn) v = __ldg(reinterpret_cast<const float4*>(a.x + ((size_t)(sg.w0 + r) * a.P + pix) * a.ldx) + l16);
+          float s = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+          for (int o = 1; o < 16; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          const float mu = s * (1.0f / 64.f);
+          const float d0 = v.x - mu, d1 = v.y - mu, d2 = v.z - mu, d3 = v.w - mu;
+          float ss = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+#pragma unroll
+          for (int o = 1; o < 16; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+          if (r < sg.wn) {
+            if (l16 == 0) st[r] = make_float2(mu, 1.0f / sqrtf(ss * (1.0f / 64.f) + 1e-5f));
+            uint32_t h0, l0, h1, l1;
+            split_f16x2(v.x, v.y, h0, l0); split_f16x2(v.z, v.w, h1, l1);
+            const uint32_t off = swz(r, l16 >> 1) + (l16 & 1) * 8;
+            *reinterpret_cast<uint2*>(smem + XH_OFF + off) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(smem + XL_OFF + off) = make_uint2(l0, l1);
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&bars.x_ready);
+      }
+      // the statistics of this thread's row are written by other threads: wait until every compute thread has arrived
+      mbar_wait(&bars.x_ready, ui & 1);
+      const float2 stat = row_ok ? s_stat[row] : make_float2(0.f, 1.f);
+      const float fa = stat.y * a.inv_wscale, fb = -stat.y * stat.x;
+      const float* rotp = a.rot + (size_t)(sg.w0 + (row_ok ? row : T.r0)) * 32;
+      float inv_l = 1.f;
+
+      for (int h = 0; h < 8; ++h, ++it) {
+        // table of this head for the softmax of this warpgroup (previous head's readers are done: they arrived on p_ready before
+        // anyone could pass o_ready)
+        if (hq[j]) *reinterpret_cast<float4*>(tb + 4 * wgtid) = __ldg(reinterpret_cast<const float4*>(a.table + h * kTtcTable) + wgtid);
+
+        // -------------------------------------------------------------- E1: projection accumulator -> Q_h, K_h, V_h^T
+        if (act[j]) {
+          mbar_wait(&bars.proj_ready[j], nact[j] & 1);
+          tc_fence_after();
+          uint32_t rq[32], rk[32], rv[32];
+          const uint32_t ta = tmem_base + lane_addr + s_col(j);
+          tmem_ld32_async(ta, rq); tmem_ld32_async(ta + 32, rk); tmem_ld32_async(ta + 64, rv);
+          tmem_wait_ld();
+          // K/V/Q of the previous head may still be read by the other tile's S / PV
+          if (nq[1 - j] > 0) mbar_wait(&bars.o_ready[1 - j], (nq[1 - j] - 1) & 1);
+          if (dbg && h == 0 && row_ok) {
+            float* d = a.dbg + (size_t)row * 96;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { d[i] = __uint_as_float(rq[i]); d[32 + i] = __uint_as_float(rk[i]); d[64 + i] = __uint_as_float(rv[i]); }
+          }
+          if (row_ok) {
+            const float faq = fa * LOG2E, fbq = fb * LOG2E;         // scores live in the log2 domain
+            const float* wsq = ws + h * 32;
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              float q8[8], k8[8];
+              const float4 cs0 = __ldg(reinterpret_cast<const float4*>(rotp) + 2 * c8);        // (cos, sin) of pairs 4 c8, 4 c8 + 1
+              const float4 cs1 = __ldg(reinterpret_cast<const float4*>(rotp) + 2 * c8 + 1);    // pairs 4 c8 + 2, 4 c8 + 3
+              const float cs[8] = {cs0.x, cs0.y, cs0.z, cs0.w, cs1.x, cs1.y, cs1.z, cs1.w};
+#pragma unroll
+              for (int pp = 0; pp < 4; ++pp) {
+                const int i = c8 * 8 + 2 * pp;
+                const float q0 = fmaf(fbq, wsq[i], faq * __uint_as_float(rq[i]));
+                const float q1 = fmaf(fbq, wsq[i + 1], faq * __uint_as_float(rq[i + 1]));
+                const float k0 = fmaf(fb, wsq[256 + i], fa * __uint_as_float(rk[i]));
+                const float k1 = fmaf(fb, wsq[256 + i + 1], fa * __uint_as_float(rk[i + 1]));
+                const float co = cs[2 * pp], si = cs[2 * pp + 1];
+                q8[2 * pp] = q0 * co - q1 * si; q8[2 * pp + 1] = q1 * co + q0 * si;
+                k8[2 * pp] = k0 * co - k1 * si; k8[2 * pp + 1] = k1 * co + k0 * si;
+              }
+              store_row_chunk(smem + Q_OFF, row, c8, q8);
+              store_row_chunk(smem + K_OFF, row, c8, k8);
+            }
+            // V_h^T: element (dim d, key = row) of chunk row >> 6
+            uint8_t* vh = smem + VH_OFF + (row >> 6) * 4096 + (row & 7) * 2;
+            uint8_t* vl = smem + VL_OFF + (row >> 6) * 4096 + (row & 7) * 2;
+            const int cc = (row & 63) >> 3;
+#pragma unroll
+            for (int d = 0; d < 32; ++d) {
+              const float v = fmaf(fb, wsq[512 + d], fa * __uint_as_float(rv[d]));
+              uint16_t hi, lo;
+              split_f16(v, hi, lo);
+              const uint32_t off = swz(d, cc);
+              *reinterpret_cast<uint16_t*>(vh + off) = hi;
+              *reinterpret_cast<uint16_t*>(vl + off) = lo;
+            }
+          }
+          tc_fence_before();
+          fence_proxy_async();
+          ++nact[j];
+        } else if (nq[1 - j] > 0) {
+          // nothing to write, but keep the ordering argument simple: no early arrival before the other tile's reads are done
+          mbar_wait(&bars.o_ready[1 - j], (nq[1 - j] - 1) & 1);
+        }
+        mbar_arrive(&bars.kv_ready);
+
+        if (hq[j]) {
+          named_bar(1 + j, 128);                                   // table staged by all 128 threads of this warpgroup
+          // ------------------------------------------------------------ E2: softmax of this thread's row
+          mbar_wait(&bars.s_ready[j], nq[j] & 1);
+          tc_fence_after();
+          int xw = T.r0 + 32 * wq - band - T.kb;
+          if (xw < 0) xw = 0;
+          int cstart = xw & ~15;
+          if (cstart > SN - CW) cstart = SN - CW;
+          const int rowc = row < WMAX - 1 ? row : WMAX - 1;
+          const float* tp = tb + (T.kb + cstart - rowc + kTtcTableZero);
+          const int climit = (sg.wn < T.kb + SN ? sg.wn : T.kb + SN) - T.kb - cstart;      // columns whose key lies inside the window
+          const uint32_t ts = tmem_base + lane_addr + s_col(j);
+          uint32_t sv[128];
+          {
+            uint32_t (*sv4)[32] = reinterpret_cast<uint32_t (*)[32]>(sv);
+            tmem_ld32_async(ts + cstart, sv4[0]); tmem_ld32_async(ts + cstart + 32, sv4[1]);
+            tmem_ld32_async(ts + cstart + 64, sv4[2]); tmem_ld32_async(ts + cstart + 96, sv4[3]);
+            tmem_wait_ld();
+          }
+          if (dbg && h == 0 && row_ok) {
+            float* d = a.dbg + (size_t)WMAX * 96 + (size_t)row * 130;
+            d[0] = (float)(T.kb + cstart); d[1] = (float)climit;
+#pragma unroll
+            for (int c = 0; c < 128; ++c) d[2 + c] = __uint_as_float(sv[c]);
+          }
+          float m = -1e30f;
+          if (climit >= CW) {
+#pragma unroll
+            for (int c = 0; c < CW; ++c) {
+              const float s = __uint_as_float(sv[c]) + tp[c];
+              sv[c] = __float_as_uint(s);
+              m = fmaxf(m, s);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < CW; ++c) {
+              const float s = (c < climit) ? __uint_as_float(sv[c]) + tp[c] : -1e30f;
+              sv[c] = __float_as_uint(s);
+              m = fmaxf(m, s);
+            }
+          }
+          float lsum = 0.f;
+          uint32_t ph[64], pl[64];
+#pragma unroll
+          for (int c = 0; c < CW; c += 2) {
+            const float p0 = ex2f(__uint_as_float(sv[c]) - m), p1 = ex2f(__uint_as_float(sv[c + 1]) - m);
+            lsum += p0 + p1;
+            split_f16x2(p0, p1, ph[c >> 1], pl[c >> 1]);
+          }
+          inv_l = 1.0f / lsum;
+          // P (fp16 pairs) over the S columns: hi at [0, 80), lo at [80, 160); zeros outside this warp's 128-key span
+          const uint32_t c2 = (uint32_t)(cstart >> 1);
+          tmem_st32(ts + c2, ph, 0); tmem_st32(ts + c2 + 32, ph, 32);
+          tmem_st32(ts + 80 + c2, pl, 0); tmem_st32(ts + 80 + c2 + 32, pl, 32);
+#pragma unroll
+          for (int b = 0; b < 10; ++b) {
+            if (8 * b < (int)c2 || 8 * b >= (int)c2 + 64) { tmem_st8_zero(ts + 8 * b); tmem_st8_zero(ts + 80 + 8 * b); }
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&bars.p_ready[j]);
+
+          // ------------------------------------------------------------ E3: O / rowsum -> O_h
+          mbar_wait(&bars.o_ready[j], nq[j] & 1);
+          tc_fence_after();
+          {
+            uint32_t ro[32];
+            tmem_ld32_async(tmem_base + lane_addr + o_col(j), ro);
+            tmem_wait_ld();
+            if (dbg && h == 0 && row_ok) {
+              float* d = a.dbg + (size_t)WMAX * (96 + 130) + (size_t)row * 33;
+              d[0] = lsum;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) d[1 + i] = __uint_as_float(ro[i]);
+            }
+            if (row_ok) {
+#pragma unroll
+              for (int c8 = 0; c8 < 4; ++c8) {
+                float o8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o8[i] = __uint_as_float(ro[c8 * 8 + i]) * inv_l;
+                store_row_chunk(smem + O_OFF, row, c8, o8);
+              }
+            }
+          }
+          tc_fence_before();
+          fence_proxy_async();
+          mbar_arrive(&bars.oh_ready[j]);
+          ++nq[j];
+        }
+        if (hq[1 - j]) ++nq[1 - j];
+        if (act[1 - j]) ++nact[1 - j];
+      }
+      // the next prologue overwrites X: the other tile's last projection must have finished reading it
+      if (act[1 - j]) mbar_wait(&bars.proj_ready[1 - j], (nact[1 - j] - 1) & 1);
+
+      // ------------------------------------------------------------------ unit epilogue: out = residual + Y
+      if (hq[j]) {
+        mbar_wait(&bars.y_ready[j], (nq[j] / 8 - 1) & 1);        // y_ready completes once per unit with queries
+        tc_fence_after();
+        uint32_t ry[64];
+        {
+          uint32_t (*ry2)[32] = reinterpret_cast<uint32_t (*)[32]>(ry);
+          tmem_ld32_async(tmem_base + lane_addr + y_col(j), ry2[0]);
+          tmem_ld32_async(tmem_base + lane_addr + y_col(j) + 32, ry2[1]);
+          tmem_wait_ld();
+        }
+        if (row >= T.q0 && row < T.q1) {
+          const size_t orow = (size_t)(sg.w0 + row - a.q_lo) * a.P + pix;
+          const float4* rp = reinterpret_cast<const float4*>(a.res + orow * a.ldr);
+          float4* op = reinterpret_cast<float4*>(a.out + orow * a.ldo);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 r = rp[i];
+            op[i] = make_float4(fmaf(__uint_as_float(ry[4 * i]), a.inv_oscale, r.x), fmaf(__uint_as_float(ry[4 * i + 1]), a.inv_oscale, r.y),
+                                fmaf(__uint_as_float(ry[4 * i + 2]), a.inv_oscale, r.z), fmaf(__uint_as_float(ry[4 * i + 3]), a.inv_oscale, r.w));
+          }
+        }
+        tc_fence_before();
+      }
+    }
+  } else if (warp == LOAD_WARP) {
+    // ======================================================================= weight loader
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        for (int h = 0; h < 8; ++h, ++it) {
+          mbar_wait(&bars.wq_free, (it & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars.wq_ready, WQ_BYTES);
+          bulk_copy_g2s(smem + WQ_OFF, a.Wqkv + (size_t)h * WQ_BYTES, WQ_BYTES, &bars.wq_ready);
+          mbar_wait(&bars.wo_free, (it & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars.wo_ready, WO_BYTES);
+          bulk_copy_g2s(smem + WO_OFF, a.Wout + (size_t)h * WO_BYTES, WO_BYTES, &bars.wo_ready);
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ======================================================================= MMA issuer
+    if (lane == 0) {
+      const uint32_t sb = smem_u32(smem);
+      uint32_t it = 0, ui = 0, nq[2] = {0, 0};
+      constexpr uint32_t ID96 = idesc_n(96), ID160 = idesc_n(SN), ID32 = idesc_n(32), ID64 = idesc_n(64);
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ui) {
+        const int pix = u / a.nseg;
+        const TtcSegment sg = a.seg[u - pix * a.nseg];
+        TtcTile tl[2];
+        ttc_tiles(sg, band, tl);
+        const bool act[2] = {tl[0].r1 > tl[0].r0, tl[1].r1 > tl[1].r0};
+        const bool hq[2] = {tl[0].q1 > tl[0].q0, tl[1].q1 > tl[1].q0};
+
+        auto issue_proj = [&](uint32_t itn) {
+          mbar_wait(&bars.wq_ready, itn & 1);
+          tc_fence_after();
+          for (int j = 0; j < 2; ++j) {
+            if (!act[j]) continue;
+            const uint32_t ro = (uint32_t)(tl[j].r0 >> 3) * 1024u;
+            const uint64_t ahi = make_desc(sb + XH_OFF + ro), alo = make_desc(sb + XL_OFF + ro);
+            const uint64_t bhi = make_desc(sb + WQ_OFF), blo = make_desc(sb + WQ_OFF + 96 * 128);
+            const uint32_t d = tmem_base + s_col(j);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t o = (uint64_t)(2 * ks);
+              tc_mma_f16(d, alo + o, bhi + o, ID96, ks ? 1u : 0u);
+              tc_mma_f16(d, ahi + o, blo + o, ID96, 1u);
+              tc_mma_f16(d, ahi + o, bhi + o, ID96, 1u);
+            }
+            tc_commit(&bars.proj_ready[j]);
+          }
+          tc_commit(&bars.wq_free);
+        };
+
+        mbar_wait(&bars.x_ready, ui & 1);
+        fence_proxy_async();
+        issue_proj(it);
+        for (int h = 0; h < 8; ++h, ++it) {
+          mbar_wait(&bars.kv_ready, it & 1);
+          fence_proxy_async();
+          tc_fence_after();
+          for (int j = 0; j < 2; ++j) {
+            if (!hq[j]) continue;
+            const uint64_t qd = make_desc(sb + Q_OFF + (uint32_t)(tl[j].r0 >> 3) * 1024u);
+            const uint64_t kd = make_desc(sb + K_OFF + (uint32_t)(tl[j].kb >> 3) * 1024u);
+            const uint32_t d = tmem_base + s_col(j);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t hi = (uint64_t)(2 * ks), lo = (uint64_t)(4 + 2 * ks);
+              tc_mma_f16(d, qd + lo, kd + hi, ID160, ks ? 1u : 0u);
+              tc_mma_f16(d, qd + hi, kd + lo, ID160, 1u);
+              tc_mma_f16(d, qd + hi, kd + hi, ID160, 1u);
+            }
+            tc_commit(&bars.s_ready[j]);
+          }
+          for (int j = 0; j < 2; ++j) {
+            if (!hq[j]) continue;
+            mbar_wait(&bars.p_ready[j], nq[j] & 1);
+            tc_fence_after();
+            const uint32_t pa = tmem_base + s_col(j), d = tmem_base + o_col(j);
+#pragma unroll
+            for (int s = 0; s < SN / 16; ++s) {
+              const int key = tl[j].kb + 16 * s;
+              const uint32_t vo = (uint32_t)(key >> 6) * 4096u + (uint32_t)(key & 63) * 2u;
+              const uint64_t vh = make_desc(sb + VH_OFF + vo), vl = make_desc(sb + VL_OFF + vo);
+              tc_mma_f16_ts(d, pa + 80 + 8 * s, vh, ID32, s ? 1u : 0u);
+              tc_mma_f16_ts(d, pa + 8 * s, vl, ID32, 1u);
+              tc_mma_f16_ts(d, pa + 8 * s, vh, ID32, 1u);
+            }
+            tc_commit(&bars.o_ready[j]);
+          }
+          // next head's projection goes in behind P*V (its accumulator aliases the P columns); E3 / Y of this head overlap it
+          if (h < 7) issue_proj(it + 1);
+          mbar_wait(&bars.wo_ready, it & 1);
+          for (int j = 0; j < 2; ++j) {
+            if (!hq[j]) continue;
+            mbar_wait(&bars.oh_ready[j], nq[j] & 1);
+            fence_proxy_async();
+            tc_fence_after();
+            const uint64_t od = make_desc(sb + O_OFF + (uint32_t)(tl[j].r0 >> 3) * 1024u);
+            const uint64_t wd = make_desc(sb + WO_OFF);
+            const uint32_t d = tmem_base + y_col(j);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t hi = (uint64_t)(2 * ks), lo = (uint64_t)(4 + 2 * ks);
+              tc_mma_f16(d, od + lo, wd + hi, ID64, (h || ks) ? 1u : 0u);
+              tc_mma_f16(d, od + hi, wd + lo, ID64, 1u);
+              tc_mma_f16(d, od + hi, wd + hi, ID64, 1u);
+            }
+            if (h == 7) tc_commit(&bars.y_ready[j]);
+            ++nq[j];
+          }
+          tc_commit(&bars.wo_free);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+}  // namespace
+
+bool temporal_tc_supported(int C, int F, int band, int q_lo, int q_hi) {
+  if (C != 64 || band < 1 || band > kTtcBandMax || F < 1 || q_lo < 0 || q_hi > F || q_lo >= q_hi) return false;
+  TtcSegment seg[kTtcMaxSeg];
+  return temporal_tc_plan(F, band, q_lo, q_hi, seg) > 0;
+}
+
+int temporal_tc_plan(int F, int band, int q_lo, int q_hi, TtcSegment* seg) {
+  if (F <= kTtcWindowMax) {
+    seg[0] = TtcSegment{0, F, q_lo, q_hi};
+    return 1;
+  }
+  const int qmax = kTtcWindowMax - 2 * band;                  // queries per segment when the window needs a halo on both sides
+  const int nq = q_hi - q_lo;
+  const int nseg = (nq + qmax - 1) / qmax;
+  if (nseg > kTtcMaxSeg) return 0;
+  for (int s = 0; s < nseg; ++s) {
+    const int qa = q_lo + (int)((long long)nq * s / nseg), qb = q_lo + (int)((long long)nq * (s + 1) / nseg);
+    const int w0 = std::max(0, qa - band), w1 = std::min(F, qb + band);
+    if (w1 - w0 > kTtcWindowMax) return 0;
+    seg[s] = TtcSegment{w0, w1 - w0, qa, qb};
+  }
+  return nseg;
+}
+
+int launch_temporal_tc(const TemporalTcArgs& a_in, cudaStream_t st) {
+  TemporalTcArgs a = a_in;
+  if (a.band < 1 || a.band > kTtcBandMax) { set_last_error("temporal_tc: unsupported band"); return -1; }
+  a.nseg = temporal_tc_plan(a.F, a.band, a.q_lo, a.q_hi, a.seg);
+  if (a.nseg <= 0) { set_last_error("temporal_tc: unsupported shape"); return -1; }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    DAWN_CUDA_OK(cudaGetDevice(&dev));
+    DAWN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    DAWN_CUDA_OK(cudaFuncSetAttribute(temporal_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
+  }
+  const int grid = std::min(a.P * a.nseg, num_sms);
+  temporal_tc_kernel<<<grid, NTH, SMEM_DYN, st>>>(a);
+  DAWN_LAUNCH_OK();
+  return 0;
+}
+
+// Host packing.  wqkv: [768][64] fp32 rows = output columns (q | k | v blocks of 256, gamma and q-scale folded), wout: [64][256].
+void temporal_tc_pack(const float* wqkv, const float* wout, std::vector<uint8_t>& Wq, std::vector<uint8_t>& Wo, float* inv_wscale,
+                      float* inv_oscale) {
+  auto pow2scale = [](const float* p, size_t n) {
+    float mx = 0.f;
+    for (size_t i = 0; i < n; ++i) mx = std::max(mx, std::fabs(p[i]));
+    int e = 0;
+    if (mx > 0.f) std::frexp(mx, &e);
+    return std::ldexp(1.0f, 11 - e);
+  };
+  const float sq = pow2scale(wqkv, (size_t)768 * 64), so = pow2scale(wout, (size_t)64 * 256);
+  *inv_wscale = 1.0f / sq; *inv_oscale = 1.0f / so;
+  auto put = [](uint8_t* hi, uint8_t* lo, float v) {
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    memcpy(hi, &h, 2); memcpy(lo, &l, 2);
+  };
+  auto swz_h = [](int r, int c) { return (size_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); };
+  Wq.assign((size_t)8 * WQ_BYTES, 0);
+  Wo.assign((size_t)8 * WO_BYTES, 0);
+  for (int h = 0; h < 8; ++h) {
+    uint8_t* qh = Wq.data() + (size_t)h * WQ_BYTES; uint8_t* ql = qh + 96 * 128;
+    for (int part = 0; part < 3; ++part)
+      for (int r = 0; r < 32; ++r)
+        for (int k = 0; k < 64; ++k) {
+          const int n = part * 32 + r;
+          const size_t off = swz_h(n, k >> 3) + (size_t)(k & 7) * 2;
+          put(qh + off, ql + off, wqkv[(size_t)(part * 256 + h * 32 + r) * 64 + k] * sq);
+        }
+    uint8_t* oi = Wo.data() + (size_t)h * WO_BYTES;
+    for (int c = 0; c < 64; ++c)
+      for (int d = 0; d < 32; ++d) {
+        const size_t ohi = swz_h(c, d >> 3) + (size_t)(d & 7) * 2, olo = swz_h(c, 4 + (d >> 3)) + (size_t)(d & 7) * 2;
+        put(oi + ohi, oi + olo, wout[(size_t)c * 256 + h * 32 + d] * so);
+      }
+  }
+}
+
+void temporal_tc_table(const float* bias, int band, std::vector<float>& table) {
+  table.assign((size_t)8 * kTtcTable, -1e30f);
+  for (int h = 0; h < 8; ++h)
+    for (int rel = -band; rel <= band; ++rel)
+      table[(size_t)h * kTtcTable + kTtcTableZero + rel] = bias[(size_t)h * (2 * band + 1) + rel + band] * 1.4426950408889634f;
+}
+
+}  // namespace dawn

@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "tc_gemm.cuh"
 #include "temporal_fused.cuh"
+#include "temporal_tc.cuh"
 #include "sla_fused.cuh"
 #include "ca_fused.cuh"
 #include "sampler.cuh"
@@ -118,6 +119,8 @@ struct AttnW {     // temporal attention / mid spatial attention (U:648-725)
   int C = 0; float Wqkv_scale = 1.f; float *Wqkv = nullptr, *wsum = nullptr, *Wqkv_img = nullptr; ConvW out;
   // fused per-pixel kernel (temporal_fused.cu), 64-channel levels only
   uint16_t *fq = nullptr, *fo = nullptr; float f_inv_wscale = 1.f, f_inv_oscale = 1.f;
+  // tcgen05 kernel (temporal_tc.cu): swizzled shared-memory images per head
+  uint8_t *tq = nullptr, *to = nullptr; float t_inv_wscale = 1.f, t_inv_oscale = 1.f;
 };
 struct SlaW {      // spatial linear attention (U:602-627)
   int C = 0; float Wqkv_scale = 1.f; float *Wqkv = nullptr, *wsum = nullptr, *Wqkv_img = nullptr, *WoutT = nullptr, *bout = nullptr;
@@ -145,6 +148,7 @@ struct dawn_unet {
   bool use_presplit = true;                    // fp16 hi|lo pre-split of A for multi-n-tile 3x3 convs (DAWN_PRESPLIT=0: off)
   bool use_fused_ca = true;                    // fused cross-attention gate kernel for ci <= 128 (DAWN_FUSED_CA=0: unfused)
   bool use_fused_sla = true;                   // fused SLA context on 64-channel levels (DAWN_FUSED_SLA=0: unfused)
+  bool use_ta_tc = true;                       // tcgen05 temporal attention on 64-channel levels (DAWN_TA_TC=0: mma.sync kernel)
   bool use_fused_ta = true;                    // fused per-pixel temporal attention on 64-channel levels (DAWN_FUSED_TA=0: unfused)
   bool use_attn_tc = true;                     // tensor-core attention core (DAWN_ATTN_TC=0 falls back to SIMT)
 
@@ -157,6 +161,7 @@ struct dawn_unet {
   int cin_pad = 0;
   float *time_freqs = nullptr, *tW1 = nullptr, *tb1 = nullptr, *tW2 = nullptr, *tb2 = nullptr;
   float *rel_bias = nullptr, *rot_freqs = nullptr;
+  float* ttc_table = nullptr;                  // [8][kTtcTable] bias * log2(e) inside the band, -1e30 outside (temporal_tc.cu)
   std::vector<ResBlockW> rb;                   // all resnet blocks
   std::map<std::string, int> rb_index;
   AttnW init_ta, mid_sa, mid_ta;
@@ -398,6 +403,13 @@ int pack_attn(dawn_unet* h, const std::string& norm_name, const std::string& fn,
     memcpy(tq.data(), Wq.data(), Wq.size() * 2); memcpy(to.data(), Wo.data(), Wo.size() * 2);
     DAWN_TRY(dev_upload(h, tq, &dq)); DAWN_TRY(dev_upload(h, to, &dout));
     a->fq = reinterpret_cast<uint16_t*>(dq); a->fo = reinterpret_cast<uint16_t*>(dout);
+    std::vector<uint8_t> Tq, To;
+    temporal_tc_pack(wq.data(), o->data.data(), Tq, To, &a->t_inv_wscale, &a->t_inv_oscale);
+    std::vector<float> uq(Tq.size() / 4), uo(To.size() / 4);
+    memcpy(uq.data(), Tq.data(), Tq.size()); memcpy(uo.data(), To.data(), To.size());
+    float *dtq = nullptr, *dto = nullptr;
+    DAWN_TRY(dev_upload(h, uq, &dtq)); DAWN_TRY(dev_upload(h, uo, &dto));
+    a->tq = reinterpret_cast<uint8_t*>(dtq); a->to = reinterpret_cast<uint8_t*>(dto);
   }
   return 0;
 }
@@ -726,6 +738,27 @@ int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const st
     }
     DAWN_NCCL_OK(g_nccl.GroupEnd());
     xe = Act{h->XE, x.C, x.C, x.H, x.W};
+  }
+  if (h->use_ta_tc && w.tq && h->ttc_table && temporal_tc_supported(x.C, Fe, h->cfg.win_width, hl, hl + F)) {
+    // long sequences are cut into segments whose windows overlap: an in-place layer would let one segment read rows another already
+    // replaced, so the input is copied aside first (sharded runs already read from the halo-extended copy)
+    if (Fe > kTtcWindowMax && xe.p == dst.p) {
+      h->launches++;
+      DAWN_CUDA_OK(cudaMemcpy2DAsync(h->XE, (size_t)x.C * sizeof(float), x.p, (size_t)x.ld * sizeof(float), (size_t)x.C * sizeof(float),
+                                     (size_t)F * P, cudaMemcpyDeviceToDevice, c.st));
+      xe = Act{h->XE, x.C, x.C, x.H, x.W};
+    }
+    TemporalTcArgs a{};
+    a.x = xe.p; a.ldx = xe.ld; a.res = x.p; a.ldr = x.ld; a.out = dst.p; a.ldo = dst.ld;
+    a.F = Fe; a.P = P; a.q_lo = hl; a.q_hi = hl + F;
+    a.Wqkv = w.tq; a.Wout = w.to; a.wsum = w.wsum; a.rot = h->ROT; a.table = h->ttc_table; a.band = h->cfg.win_width;
+    a.inv_wscale = w.t_inv_wscale; a.inv_oscale = w.t_inv_oscale;
+    double pairs = 0;
+    for (int i = hl; i < hl + F; ++i) pairs += std::min(Fe - 1, i + a.band) - std::max(0, i - a.band) + 1;
+    ProfScope ps(c, x.H == h->lH[0] ? PC_TEMPORAL_L0 : PC_ATTN_CORE, 2.0 * Me * x.C * 768 + 4.0 * 32 * 8 * P * pairs + 2.0 * F * P * 256 * x.C,
+                 4.0 * (Me + 2.0 * F * P) * x.C);
+    DAWN_TRY(launch_temporal_tc(a, c.st));
+    return tap(c, name, dst);
   }
   if (h->use_fused_ta && w.fq && temporal_fused_supported(x.C, Fe, h->cfg.win_width, hl, hl + F)) {
     TemporalFusedArgs a{};
@@ -1069,6 +1102,7 @@ int dawn_unet_create(const dawn_unet_cfg* cfg, dawn_unet** out) {
   { const char* e = getenv("DAWN_TC"); h->use_tc = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_ATTN_TC"); h->use_attn_tc = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_FUSED_TA"); h->use_fused_ta = !(e && e[0] == '0'); }
+  { const char* e = getenv("DAWN_TA_TC"); h->use_ta_tc = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_FUSED_SLA"); h->use_fused_sla = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_FUSED_CA"); h->use_fused_ca = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_PRESPLIT"); h->use_presplit = !(e && e[0] == '0'); }
@@ -1133,6 +1167,14 @@ int dawn_unet_commit_params(dawn_unet* h) {
   }
   DAWN_TRY(upload_raw(h, "aux.time_freqs", {dim / 2}, &h->time_freqs));
   DAWN_TRY(upload_raw(h, "aux.rel_bias", {8, 2 * cfg.win_width + 1}, &h->rel_bias));
+  h->ttc_table = nullptr;
+  if (cfg.win_width >= 1 && cfg.win_width <= kTtcBandMax) {
+    const HostParam* rb;
+    DAWN_TRY(need(h, "aux.rel_bias", {8, 2 * cfg.win_width + 1}, &rb));
+    std::vector<float> tab;
+    temporal_tc_table(rb->data.data(), cfg.win_width, tab);
+    DAWN_TRY(dev_upload(h, tab, &h->ttc_table));
+  }
   DAWN_TRY(upload_raw(h, "time_mlp.1.weight", {h->tdim, dim}, &h->tW1));
   DAWN_TRY(upload_raw(h, "time_mlp.1.bias", {h->tdim}, &h->tb1));
   DAWN_TRY(upload_raw(h, "time_mlp.3.weight", {h->tdim, h->tdim}, &h->tW2));

@@ -138,6 +138,11 @@ int dawn_selftest_tc_gemm(int F, int H, int W, int Cin, int N, int ksize, int wi
  * temporal != 0: nseq pixel sequences of L frames, band 40 with bias; else nseq frames of L tokens, full attention */
 int dawn_selftest_attention(int nseq, int L, int temporal, float* max_abs_diff, float* max_abs_ref);
 
+/* self-test of the tcgen05 temporal-attention kernel (64-channel levels) on random data: err[0] projection accumulator (relative),
+ * err[1] scores, err[2] attention output, err[3] layer output of pixel 0 (all absolute, against a double-precision host computation),
+ * err[4] all pixels against the mma.sync kernel (-1 where it does not support the shape), err[5] NaN count. */
+int dawn_selftest_temporal_tc(int F, int P, int band, int q_lo, int q_hi, float* err, float* max_abs_ref);
+
 const char* dawn_last_error(void);
 const char* dawn_build_info(void);
 

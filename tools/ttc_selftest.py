@@ -1,0 +1,42 @@
+"""GPU: tcgen05 temporal attention (temporal_tc.cu) stage by stage against a host computation and against the mma.sync kernel;
+each case in its own time-boxed subprocess (a hung kernel must not take the whole call down)."""
+import ctypes
+import subprocess
+import sys
+
+CASES = [  # F, P, band, q_lo, q_hi
+    (16, 4, 40, 0, 16),
+    (96, 8, 40, 0, 96),
+    (200, 16, 40, 0, 200),
+    (23, 3, 40, 0, 23),
+    (1, 2, 40, 0, 1),
+    (81, 5, 40, 0, 81),
+    (64, 9, 8, 0, 64),
+    (180, 6, 40, 40, 140),       # shard with halos on both sides (100 owned frames)
+    (224, 6, 40, 0, 224),
+    (280, 300, 40, 40, 240),     # two segments, more units than SMs
+    (400, 7, 40, 0, 400),        # long single-GPU clip: three segments
+    (200, 4096, 40, 0, 200),     # the bench shape of one level-0 layer
+]
+
+
+def one(args):
+    sys.path.insert(0, ".")
+    from dawn_pytorch_b200 import _lib
+    err = (ctypes.c_float * 6)()
+    mr = ctypes.c_float()
+    rc = _lib.lib.dawn_selftest_temporal_tc(*args, err, ctypes.byref(mr))
+    print(f"ttc {args}: rc={rc} proj_rel={err[0]:.2e} S={err[1]:.2e} O={err[2]:.2e} out_pix0={err[3]:.2e} vs_mma_sync={err[4]:.2e} "
+          f"nan={int(err[5])} max|ref|={mr.value:.2f}" + ("" if rc == 0 else " ERR " + _lib.lib.dawn_last_error().decode()), flush=True)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        one(tuple(int(a) for a in sys.argv[1:]))
+    else:
+        for c in CASES:
+            try:
+                r = subprocess.run([sys.executable, __file__, *map(str, c)], timeout=120, capture_output=True, text=True)
+                print(r.stdout.strip() or ("NO OUTPUT rc=%d %s" % (r.returncode, r.stderr[-400:])), flush=True)
+            except subprocess.TimeoutExpired:
+                print(f"ttc {c}: TIMEOUT (hang)", flush=True)
