@@ -94,15 +94,15 @@ __global__ void threshold_kernel(const uint32_t* state, const unsigned long long
   *s_out = fmaxf(q, 1.0f);
 }
 
-// img = clamp(x0, -s, s)/s * sqrt(a_next) + c * eps + sigma * noise
+// img = clamp(x0, -s, s)/s * sqrt(a_next) + c * eps + sigma * noise;  clamp == 0: x0 is used as predicted (clip_denoised=False, U:1183)
 __global__ void ddim_update_kernel(float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
                                    const float* __restrict__ s_ptr, float ca, float cb, float sqrt_an, float c, float sigma,
-                                   long long n) {
+                                   long long n, int clamp) {
   const float s = s_ptr ? *s_ptr : 1.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float e = eps[i];
     float x0 = ca * x[i] - cb * e;
-    x0 = fminf(fmaxf(x0, -s), s) / s;
+    if (clamp) x0 = fminf(fmaxf(x0, -s), s) / s;
     float v = x0 * sqrt_an + c * e;
     if (noise) v += sigma * noise[i];
     x[i] = v;
@@ -150,7 +150,7 @@ int ddim_step_impl(float* x, const float* eps, const float* noise, int64_t n_loc
     threshold_kernel<<<1, 1, 0, st>>>(state, count_le, min_gt, lo, hi, w, s_out);
     s_ptr = s_out;
   }
-  ddim_update_kernel<<<blocks, threads, 0, st>>>(x, eps, noise, s_ptr, ca, cb, sqrt_an, c, sigma, n);
+  ddim_update_kernel<<<blocks, threads, 0, st>>>(x, eps, noise, s_ptr, ca, cb, sqrt_an, c, sigma, n, q < 0.f ? 0 : 1);
   DAWN_LAUNCH_OK();
   return 0;
 }

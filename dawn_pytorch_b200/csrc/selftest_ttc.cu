@@ -12,7 +12,24 @@
 
 using namespace dawn;
 
-extern "C" int dawn_selftest_temporal_tc(int F, int P, int band, int q_lo, int q_hi, float* err, float* max_abs_ref) {
+// Host-side view of the kernel's work decomposition (no GPU needed): segments of a sequence and the two row tiles of each.
+// out: per segment 14 ints {w0, wn, qa, qb, tile0{r0, r1, q0, q1, kb}, tile1{...}}; returns the segment count (0 = unsupported).
+extern "C" int dawn_temporal_tc_plan(int F, int band, int q_lo, int q_hi, int* out) {
+  if (band < 1 || band > kTtcBandMax || F < 1 || q_lo < 0 || q_hi > F || q_lo >= q_hi) return 0;
+  TtcSegment seg[kTtcMaxSeg];
+  const int n = temporal_tc_plan(F, band, q_lo, q_hi, seg);
+  for (int s = 0; s < n && out; ++s) {
+    TtcTile t[2];
+    ttc_tiles(seg[s], band, t);
+    int* o = out + 14 * s;
+    o[0] = seg[s].w0; o[1] = seg[s].wn; o[2] = seg[s].qa; o[3] = seg[s].qb;
+    for (int j = 0; j < 2; ++j) { o[4 + 5 * j] = t[j].r0; o[5 + 5 * j] = t[j].r1; o[6 + 5 * j] = t[j].q0; o[7 + 5 * j] = t[j].q1; o[8 + 5 * j] = t[j].kb; }
+  }
+  return n;
+}
+
+extern "C" int dawn_selftest_temporal_tc(int F, int P, int band, int q_lo, int q_hi, float* err, float* max_abs_ref, unsigned long long* trace48,
+                                         float* ms) {
   if (!err || !max_abs_ref) { set_last_error("null argument"); return -1; }
   for (int i = 0; i < 6; ++i) err[i] = -1.f;
   if (!temporal_tc_supported(64, F, band, q_lo, q_hi)) { set_last_error("selftest: unsupported shape"); return -1; }
@@ -66,6 +83,22 @@ extern "C" int dawn_selftest_temporal_tc(int F, int P, int band, int q_lo, int q
   a.Wqkv = dWq; a.Wout = dWo; a.wsum = dws; a.rot = drot; a.table = dtab; a.band = band; a.inv_wscale = iw; a.inv_oscale = io; a.dbg = ddbg;
   int rc = launch_temporal_tc(a, 0);
   if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) { set_last_error(std::string("selftest tc: ") + cudaGetErrorString(cudaGetLastError())); rc = -2; }
+  if (rc == 0 && trace48 && ms) {
+    // second, timed run without the debug dump and with the cycle trace of CTA 0
+    unsigned long long* dtr = nullptr;
+    if (!dalloc(48 * 8, (void**)&dtr)) { cleanup(); set_last_error("selftest: cudaMalloc failed"); return -2; }
+    cudaMemset(dtr, 0, 48 * 8);
+    TemporalTcArgs t = a;
+    t.dbg = nullptr; t.trace = dtr;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, 0);
+    rc = launch_temporal_tc(t, 0);
+    cudaEventRecord(e1, 0);
+    if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) { set_last_error(std::string("selftest tc(2): ") + cudaGetErrorString(cudaGetLastError())); rc = -2; }
+    if (rc == 0) { cudaEventElapsedTime(ms, e0, e1); cudaMemcpy(trace48, dtr, 48 * 8, cudaMemcpyDeviceToHost); }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
   bool have_old = false;
   if (rc == 0 && temporal_fused_supported(64, F, band, q_lo, q_hi)) {
     TemporalFusedArgs b{};

@@ -179,6 +179,9 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
     const float* ws = reinterpret_cast<const float*>(smem + WS_OFF);
     uint32_t it = 0, ui = 0;                               // head iterations / units done by this CTA
     uint32_t nact[2] = {0, 0}, nq[2] = {0, 0};             // completed phases of the per-tile barriers (rows exist / queries exist)
+    const bool tr = (a.trace != nullptr) && blockIdx.x == 0 && wgtid == 0;   // cycle trace of CTA 0 (one thread per warpgroup)
+    long long tc_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0;
+#define TTC_T(i) do { if (tr) { const long long t1_ = clock64(); tc_[i] += t1_ - t0; t0 = t1_; } } while (0)
 
     for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ui) {
       const int pix = u / a.nseg;
@@ -192,6 +195,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
       const bool row_ok = row < T.r1;
       const bool dbg = (a.dbg != nullptr) && u == 0;
 
+      if (tr) t0 = clock64();
       // ------------------------------------------------------------------ prologue: x rows -> LN statistics + fp16 split
       {
         const int l16 = tid & 15, rg = tid >> 4;           // 16 lanes x float4 = one 64-channel row; 16 rows per pass
@@ -223,6 +227,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
       }
       // the statistics of this thread's row are written by other threads: wait until every compute thread has arrived
       mbar_wait(&bars.x_ready, ui & 1);
+      TTC_T(0);
       const float2 stat = row_ok ? s_stat[row] : make_float2(0.f, 1.f);
       const float fa = stat.y * a.inv_wscale, fb = -stat.y * stat.x;
       const float* rotp = a.rot + (size_t)(sg.w0 + (row_ok ? row : T.r0)) * 32;
@@ -236,6 +241,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
         // -------------------------------------------------------------- E1: projection accumulator -> Q_h, K_h, V_h^T
         if (act[j]) {
           mbar_wait(&bars.proj_ready[j], nact[j] & 1);
+          TTC_T(1);
           tc_fence_after();
           uint32_t rq[32], rk[32], rv[32];
           const uint32_t ta = tmem_base + lane_addr + s_col(j);
@@ -243,6 +249,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
           tmem_wait_ld();
           // K/V/Q of the previous head may still be read by the other tile's S / PV
           if (nq[1 - j] > 0) mbar_wait(&bars.o_ready[1 - j], (nq[1 - j] - 1) & 1);
+          TTC_T(2);
           if (dbg && h == 0 && row_ok) {
             float* d = a.dbg + (size_t)row * 96;
 #pragma unroll
@@ -293,11 +300,13 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
           mbar_wait(&bars.o_ready[1 - j], (nq[1 - j] - 1) & 1);
         }
         mbar_arrive(&bars.kv_ready);
+        TTC_T(3);
 
         if (hq[j]) {
           named_bar(1 + j, 128);                                   // table staged by all 128 threads of this warpgroup
           // ------------------------------------------------------------ E2: softmax of this thread's row
           mbar_wait(&bars.s_ready[j], nq[j] & 1);
+          TTC_T(4);
           tc_fence_after();
           int xw = T.r0 + 32 * wq - band - T.kb;
           if (xw < 0) xw = 0;
@@ -356,9 +365,11 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
           tmem_wait_st();
           tc_fence_before();
           mbar_arrive(&bars.p_ready[j]);
+          TTC_T(5);
 
           // ------------------------------------------------------------ E3: O / rowsum -> O_h
           mbar_wait(&bars.o_ready[j], nq[j] & 1);
+          TTC_T(6);
           tc_fence_after();
           {
             uint32_t ro[32];
@@ -383,6 +394,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
           tc_fence_before();
           fence_proxy_async();
           mbar_arrive(&bars.oh_ready[j]);
+          TTC_T(7);
           ++nq[j];
         }
         if (hq[1 - j]) ++nq[1 - j];
@@ -394,6 +406,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
       // ------------------------------------------------------------------ unit epilogue: out = residual + Y
       if (hq[j]) {
         mbar_wait(&bars.y_ready[j], (nq[j] / 8 - 1) & 1);        // y_ready completes once per unit with queries
+        TTC_T(8);
         tc_fence_after();
         uint32_t ry[64];
         {
@@ -414,8 +427,10 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
           }
         }
         tc_fence_before();
+        TTC_T(9);
       }
     }
+    if (tr) for (int i = 0; i < 12; ++i) a.trace[16 * j + i] = (unsigned long long)tc_[i];
   } else if (warp == LOAD_WARP) {
     // ======================================================================= weight loader
     if (lane == 0) {
@@ -436,6 +451,9 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
     if (lane == 0) {
       const uint32_t sb = smem_u32(smem);
       uint32_t it = 0, ui = 0, nq[2] = {0, 0};
+      const bool tr = (a.trace != nullptr) && blockIdx.x == 0;
+      long long tc_[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0;
+      const long long t_begin = clock64();
       constexpr uint32_t ID96 = idesc_n(96), ID160 = idesc_n(SN), ID32 = idesc_n(32), ID64 = idesc_n(64);
       for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ui) {
         const int pix = u / a.nseg;
@@ -447,6 +465,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
 
         auto issue_proj = [&](uint32_t itn) {
           mbar_wait(&bars.wq_ready, itn & 1);
+          TTC_T(1);
           tc_fence_after();
           for (int j = 0; j < 2; ++j) {
             if (!act[j]) continue;
@@ -464,13 +483,17 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
             tc_commit(&bars.proj_ready[j]);
           }
           tc_commit(&bars.wq_free);
+          TTC_T(2);
         };
 
+        if (tr) t0 = clock64();
         mbar_wait(&bars.x_ready, ui & 1);
+        TTC_T(0);
         fence_proxy_async();
         issue_proj(it);
         for (int h = 0; h < 8; ++h, ++it) {
           mbar_wait(&bars.kv_ready, it & 1);
+          TTC_T(3);
           fence_proxy_async();
           tc_fence_after();
           for (int j = 0; j < 2; ++j) {
@@ -487,9 +510,11 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
             }
             tc_commit(&bars.s_ready[j]);
           }
+          TTC_T(4);
           for (int j = 0; j < 2; ++j) {
             if (!hq[j]) continue;
             mbar_wait(&bars.p_ready[j], nq[j] & 1);
+            TTC_T(5 + j);
             tc_fence_after();
             const uint32_t pa = tmem_base + s_col(j), d = tmem_base + o_col(j);
 #pragma unroll
@@ -502,13 +527,16 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
               tc_mma_f16_ts(d, pa + 8 * s, vh, ID32, 1u);
             }
             tc_commit(&bars.o_ready[j]);
+            TTC_T(7);
           }
           // next head's projection goes in behind P*V (its accumulator aliases the P columns); E3 / Y of this head overlap it
           if (h < 7) issue_proj(it + 1);
           mbar_wait(&bars.wo_ready, it & 1);
+          TTC_T(8);
           for (int j = 0; j < 2; ++j) {
             if (!hq[j]) continue;
             mbar_wait(&bars.oh_ready[j], nq[j] & 1);
+            TTC_T(9 + j);
             fence_proxy_async();
             tc_fence_after();
             const uint64_t od = make_desc(sb + O_OFF + (uint32_t)(tl[j].r0 >> 3) * 1024u);
@@ -523,12 +551,18 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
             }
             if (h == 7) tc_commit(&bars.y_ready[j]);
             ++nq[j];
+            TTC_T(11);
           }
           tc_commit(&bars.wo_free);
         }
       }
+      if (tr) {
+        for (int i = 0; i < 12; ++i) a.trace[32 + i] = (unsigned long long)tc_[i];
+        a.trace[44] = (unsigned long long)(clock64() - t_begin); a.trace[45] = it;
+      }
     }
   }
+#undef TTC_T
   tc_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) {

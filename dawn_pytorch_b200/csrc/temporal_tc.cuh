@@ -56,6 +56,7 @@ struct TemporalTcArgs {
   int nseg;
   TtcSegment seg[kTtcMaxSeg];
   float* dbg;                     // optional: intermediates of unit 0 / head 0 (selftest)
+  unsigned long long* trace;      // optional: 48 cycle counters of CTA 0 (selftest): [0,12) warpgroup 0, [16,28) warpgroup 1, [32,46) MMA issuer
 };
 
 bool temporal_tc_supported(int C, int F, int band, int q_lo, int q_hi);

@@ -70,11 +70,17 @@ class GaussianDiffusion(nn.Module):
         return list(zip(times[:-1], times[1:]))
 
     def ddim_coefficients(self, t, t_next):
-        """Host-side scalars of one update, evaluated with the same fp32 torch arithmetic as the reference (:1170-1199)."""
-        prev = self.alphas_cumprod_prev.detach().cpu()
+        """Host-side scalars of one update, evaluated with the same fp32 torch arithmetic as the reference (:1170-1199).
+        The three schedule buffers are copied to the host once (no device reads inside the sampling loop)."""
+        tabs = getattr(self, "_host_sched", None)
+        if tabs is None or tabs[3] != (self.alphas_cumprod_prev.data_ptr(), self.alphas_cumprod_prev._version):
+            tabs = (self.alphas_cumprod_prev.detach().cpu(), self.sqrt_recip_alphas_cumprod.detach().cpu(),
+                    self.sqrt_recipm1_alphas_cumprod.detach().cpu(), (self.alphas_cumprod_prev.data_ptr(), self.alphas_cumprod_prev._version))
+            self._host_sched = tabs
+        prev = tabs[0]
         alpha, alpha_next = prev[t], prev[t_next]
-        ca = float(self.sqrt_recip_alphas_cumprod[t])
-        cb = float(self.sqrt_recipm1_alphas_cumprod[t])
+        ca = float(tabs[1][t])
+        cb = float(tabs[2][t])
         sigma = self.ddim_sampling_eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
         c = ((1 - alpha_next) - sigma ** 2).sqrt()
         return ca, cb, float(alpha_next.sqrt()), float(c), float(sigma)
@@ -107,7 +113,14 @@ class GaussianDiffusion(nn.Module):
         draw = noise_fn if noise_fn is not None else self._default_noise(unet, device, seed)
         img = draw(-1, shape).to(device).contiguous()
         n = ch * Fr * h * w
-        q = float(self.dynamic_thres_percentile) if (clip_denoised and self.use_dynamic_thres) else 0.0
+        # q > 0: dynamic threshold; q = 0: static clamp to [-1, 1]; q < 0: no clamp at all (clip_denoised=False, U:1183)
+        q = (float(self.dynamic_thres_percentile) if self.use_dynamic_thres else 0.0) if clip_denoised else -1.0
+        if tuple(shape[1:]) != (self.channels,) + tuple(shape[2:]) or fea.shape[0] != b or (cond is not None and cond.shape[0] != b):
+            raise ValueError(f"ddim_sample: shape {tuple(shape)} does not match fea {tuple(fea.shape)} / cond "
+                             f"{None if cond is None else tuple(cond.shape)} (batch) or channels {self.channels}")
+        if tuple(fea.shape[-2:]) != (h, w) or (cond is not None and cond.shape[1] != Fr):
+            raise ValueError(f"ddim_sample: fea {tuple(fea.shape)} / cond {None if cond is None else tuple(cond.shape)} do not "
+                             f"match the sample shape {tuple(shape)}")
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         guided = cond_scale != 1 and getattr(unet, "has_cond", True)
         if use_graph:

@@ -59,8 +59,11 @@ class FlowDiffusion(nn.Module):
         `pretrained_pth`; both stay optional here (`generator_params` may be given directly, weights loaded later)."""
         super().__init__()
         if is_train:
-            raise NotImplementedError("the B200 FlowDiffusion wrapper is inference-only (UVG passes model_config['is_train'] but "
-                                      "only ever samples); construct with is_train=False")
+            # config/DAWN_128.yaml / DAWN_256.yaml ship is_train: true and UVG:516 passes it straight through; in the reference it only
+            # calls .train() on unet/diffusion (FD:171-175) and UVG calls model.eval() right after.  Accept it, stay in eval mode;
+            # the training entry points (forward / p_losses) raise.
+            import warnings
+            warnings.warn("FlowDiffusion(is_train=True): the B200 wrapper is inference-only and stays in eval mode")
         self.use_residual_flow = use_residual_flow
         if generator_params is None:
             if config_pth is not None:
@@ -133,6 +136,8 @@ class FlowDiffusion(nn.Module):
         b = fea.shape[0]
         fea272 = torch.cat([fea, bbox_mask], dim=1)                                     # GaussianDiffusion.sample, U:1151
         h, w = fea272.shape[-2:]
+        if not self.diffusion.is_ddim_sampling:           # the reference's sample() would run p_sample_loop here (U:1137-1154)
+            raise NotImplementedError("only DDIM sampling (sampling_timesteps < timesteps) is implemented, as DAWN configures it")
         pred = self.diffusion.ddim_sample(fea272, (b, self.diffusion.channels, self.diffusion.num_frames, h, w), cond=ref_text,
                                           cond_scale=cond_scale, noise_fn=noise_fn, use_graph=use_graph)
         if self.use_residual_flow:

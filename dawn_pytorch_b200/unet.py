@@ -261,6 +261,10 @@ class Unet3D(nn.Module):
                 check(lib.dawn_unet_set_num_frames(self._handle, F, h, w), "dawn_unet_set_num_frames")
                 self._geom = (F, h, w)
                 self._gen = getattr(self, "_gen", 0) + 1
+            lost = getattr(self, "_shard_lost", None)
+            if lost is not None and not getattr(self, "_in_init_shard", False):
+                raise _lib.DawnError(f"frame sharding (rank {lost[0]} of {lost[1]}) was dropped by a parameter re-commit "
+                                "(.to()/.cuda()/load_state_dict after init_shard): call init_shard again on every rank")
 
     def sync_parameters(self):
         """Repack the module's parameters into kernel layouts (once per parameter change)."""
@@ -276,7 +280,11 @@ class Unet3D(nn.Module):
         check(lib.dawn_unet_commit_params(self._handle), "dawn_unet_commit_params")
         self._dirty = False
         self._gen = getattr(self, "_gen", 0) + 1
-        self._shard = None          # commit re-runs set_num_frames in the library, which leaves the handle unsharded
+        # commit re-runs set_num_frames in the library, which leaves the handle unsharded: running on would silently drop the
+        # temporal halos, the clip-wide GroupNorm statistics and the clip-wide quantile, so the next use raises instead
+        if getattr(self, "_shard", None) is not None:
+            self._shard_lost = self._shard
+        self._shard = None
         if self._geom is not None:
             self._geom = self._geom  # commit re-sized the per-clip tables for the current geometry
 
@@ -333,7 +341,16 @@ class Unet3D(nn.Module):
     def set_clip_invariants(self, fea, cond):
         """fea (channels-3, h, w) and cond (F, cond_dim) of ONE clip: everything that is constant over the
         DDIM steps (272 of the 275 init-conv input channels, all cross-attention keys/values)."""
+        if fea.dim() != 3 or cond.dim() != 2:
+            raise ValueError(f"set_clip_invariants: fea must be (channels-3, h, w) and cond (F, cond_dim); got {tuple(fea.shape)}, {tuple(cond.shape)}")
         F, (h, w) = cond.shape[0], fea.shape[-2:]
+        if fea.shape[0] != self.channels - 3 or cond.shape[1] != (self.cond_dim or 0):
+            raise ValueError(f"set_clip_invariants: expected fea with {self.channels - 3} channels and cond with {self.cond_dim} "
+                             f"features; got {tuple(fea.shape)}, {tuple(cond.shape)}")
+        if F != self.num_frames:
+            raise ValueError(f"num_frames={self.num_frames} but cond has {F} frames: call update_num_frames first (reference :925-926)")
+        if not fea.is_cuda or cond.device != fea.device:
+            raise _lib.DawnError("set_clip_invariants needs CUDA tensors on one device (no CPU fallback)")
         self._ensure(fea.device, F, h, w)
         self._fea = fea.contiguous().float()
         self._cond = cond.contiguous().float()
@@ -348,7 +365,12 @@ class Unet3D(nn.Module):
         torch.distributed) and switches the handle to sharded mode for this geometry."""
         import torch.distributed as dist
         world, rank = dist.get_world_size(), dist.get_rank()
-        self._ensure(device, F_local, h, w)
+        self._shard_lost = None
+        self._in_init_shard = True
+        try:
+            self._ensure(device, F_local, h, w)
+        finally:
+            self._in_init_shard = False
         buf = ctypes.create_string_buffer(128)
         if rank == 0:
             check(lib.dawn_nccl_unique_id(buf), "dawn_nccl_unique_id")
@@ -372,9 +394,16 @@ class Unet3D(nn.Module):
 
     def forward_x3(self, x_t, time, out=None):
         """x_t (3, F, h, w) of the clip whose invariants were set; time int64 tensor (1,) on the device."""
+        if self._geom is None or getattr(self, "_fea", None) is None:
+            raise _lib.DawnError("forward_x3: call set_clip_invariants first")
+        if tuple(x_t.shape) != (3,) + tuple(self._geom) or x_t.dtype != torch.float32 or x_t.device != self._fea.device:
+            raise ValueError(f"forward_x3: x_t must be float32 (3, {self._geom[0]}, {self._geom[1]}, {self._geom[2]}) on "
+                             f"{self._fea.device}; got {x_t.dtype} {tuple(x_t.shape)} on {x_t.device}")
         _, F, h, w = x_t.shape
         if out is None:
             out = torch.empty((self.out_dim, F, h, w), device=x_t.device, dtype=torch.float32)
+        elif tuple(out.shape) != (self.out_dim, F, h, w) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != x_t.device:
+            raise ValueError(f"forward_x3: out must be contiguous float32 ({self.out_dim}, {F}, {h}, {w}) on {x_t.device}")
         x_t = x_t.contiguous()
         with torch.cuda.device(x_t.device):
             check(lib.dawn_unet_forward_x3(self._handle, ctypes.c_void_p(x_t.data_ptr()), ctypes.c_void_p(time.data_ptr()),

@@ -107,6 +107,7 @@ int64_t dawn_unet_workspace_bytes(dawn_unet* h);
 
 /* One DDIM update around the UNet (reference GaussianDiffusion.ddim_sample :1169-1205), in place on x (device, n floats):
  *   x0 = ca*x - cb*eps;  s = max(1, quantile_q(|x0|)) over all n values (torch.quantile semantics) if q > 0, else 1;
+ *   q < 0: x0 is neither clamped nor divided (the reference's clip_denoised=False, U:1183);
  *   x = clamp(x0,-s,s)/s * sqrt_an + c*eps + sigma*noise      (noise = NULL for the last step)
  * scratch: device buffer of n + 512 32-bit words.  No host synchronisation. */
 int dawn_ddim_step(float* x, const float* eps, const float* noise, int64_t n, float ca, float cb, float sqrt_an, float c,
@@ -138,10 +139,16 @@ int dawn_selftest_tc_gemm(int F, int H, int W, int Cin, int N, int ksize, int wi
  * temporal != 0: nseq pixel sequences of L frames, band 40 with bias; else nseq frames of L tokens, full attention */
 int dawn_selftest_attention(int nseq, int L, int temporal, float* max_abs_diff, float* max_abs_ref);
 
+/* work decomposition of the tcgen05 temporal-attention kernel (host only): out receives 14 ints per segment
+ * {w0, wn, qa, qb, tile0{r0, r1, q0, q1, kb}, tile1{r0, r1, q0, q1, kb}} (room for 16 segments); returns the segment count, 0 = unsupported. */
+int dawn_temporal_tc_plan(int F, int band, int q_lo, int q_hi, int* out);
+
 /* self-test of the tcgen05 temporal-attention kernel (64-channel levels) on random data: err[0] projection accumulator (relative),
  * err[1] scores, err[2] attention output, err[3] layer output of pixel 0 (all absolute, against a double-precision host computation),
- * err[4] all pixels against the mma.sync kernel (-1 where it does not support the shape), err[5] NaN count. */
-int dawn_selftest_temporal_tc(int F, int P, int band, int q_lo, int q_hi, float* err, float* max_abs_ref);
+ * err[4] all pixels against the mma.sync kernel (-1 where it does not support the shape), err[5] NaN count.
+ * trace48 / ms (optional, both or neither): cycle counters of CTA 0 and the duration of a second, un-instrumented-output run. */
+int dawn_selftest_temporal_tc(int F, int P, int band, int q_lo, int q_hi, float* err, float* max_abs_ref, unsigned long long* trace48,
+                              float* ms);
 
 const char* dawn_last_error(void);
 const char* dawn_build_info(void);

@@ -155,5 +155,32 @@ def test_flow_diffusion_wrapper_structure_and_bbox_mask(golden_dir):
     mask = m.generate_bbox_mask(bbox, size=64)
     assert mask.shape == (1, 1, 64, 64) and float(mask.sum()) == float(g["bbox_mask_sum"])
     assert bbox[0, 0, 0] == 20.0                                  # the caller's tensor is not modified (the reference scales it in place)
+    # the shipped configs (config/DAWN_128.yaml: is_train: true) construct with is_train=True and only ever sample (UVG:516, 529):
+    # accepted with a warning, the module stays in eval mode, the training entry point raises
+    with pytest.warns(UserWarning):
+        mt = FlowDiffusion(is_train=True)
+    assert not mt.training and not mt.unet.training
     with pytest.raises(NotImplementedError):
-        FlowDiffusion(is_train=True)
+        mt(None)
+
+
+def test_fast_path_checks_shapes_before_touching_the_device():
+    """the hoisted entry takes raw pointers, so a geometry mismatch must raise instead of reading out of bounds
+    (the reference raises a broadcast error at U:925-926)."""
+    from dawn_pytorch_b200 import DynamicNfUnet3D
+    from dawn_pytorch_b200._lib import DawnError
+    from tests.gpu_common import CTOR
+    net = DynamicNfUnet3D(**CTOR).eval()
+    net.update_num_frames(8)
+    with pytest.raises(ValueError):
+        net.set_clip_invariants(torch.zeros(271, 8, 8), torch.zeros(8, 1032))         # wrong feature channels
+    with pytest.raises(ValueError):
+        net.set_clip_invariants(torch.zeros(272, 8, 8), torch.zeros(8, 1031))         # wrong cond width
+    with pytest.raises(ValueError):
+        net.set_clip_invariants(torch.zeros(272, 8, 8), torch.zeros(9, 1032))         # update_num_frames not called for 9 frames
+    with pytest.raises(ValueError):
+        net.set_clip_invariants(torch.zeros(1, 272, 8, 8), torch.zeros(8, 1032))      # batched tensor
+    with pytest.raises(DawnError):
+        net.set_clip_invariants(torch.zeros(272, 8, 8), torch.zeros(8, 1032))         # right shapes, CPU tensors: no CPU path
+    with pytest.raises(DawnError):
+        net.forward_x3(torch.zeros(3, 8, 8, 8), torch.zeros(1, dtype=torch.long))     # invariants never set

@@ -25,9 +25,20 @@ def one(args):
     from dawn_pytorch_b200 import _lib
     err = (ctypes.c_float * 6)()
     mr = ctypes.c_float()
-    rc = _lib.lib.dawn_selftest_temporal_tc(*args, err, ctypes.byref(mr))
+    tr = (ctypes.c_uint64 * 48)()
+    ms = ctypes.c_float()
+    rc = _lib.lib.dawn_selftest_temporal_tc(*args, err, ctypes.byref(mr), tr, ctypes.byref(ms))
     print(f"ttc {args}: rc={rc} proj_rel={err[0]:.2e} S={err[1]:.2e} O={err[2]:.2e} out_pix0={err[3]:.2e} vs_mma_sync={err[4]:.2e} "
-          f"nan={int(err[5])} max|ref|={mr.value:.2f}" + ("" if rc == 0 else " ERR " + _lib.lib.dawn_last_error().decode()), flush=True)
+          f"nan={int(err[5])} max|ref|={mr.value:.2f} {ms.value:.3f} ms" + ("" if rc == 0 else " ERR " + _lib.lib.dawn_last_error().decode()), flush=True)
+    if args[1] >= 1024:
+        t = list(tr)
+        names_wg = ["prologue+x_wait", "proj_wait", "E1 ld + kv_free wait", "E1 compute+arrive", "s_wait(+table bar)", "E2", "o_wait", "E3", "y_wait", "epilogue"]
+        names_mma = ["x_wait", "wq_wait", "proj issue", "kv_wait", "S issue", "p_wait0", "p_wait1", "PV issue", "wo_wait", "oh_wait0", "oh_wait1", "Y issue"]
+        its = max(t[45], 1)
+        print(f"   CTA0: {its} head iterations, MMA thread total {t[44]} cycles = {t[44] / its:.0f} per head")
+        for j in (0, 1):
+            print(f"   WG{j} cycles/head: " + ", ".join(f"{n} {t[16 * j + i] / its:.0f}" for i, n in enumerate(names_wg)))
+        print("   MMA cycles/head: " + ", ".join(f"{n} {t[32 + i] / its:.0f}" for i, n in enumerate(names_mma)))
 
 
 if __name__ == "__main__":
