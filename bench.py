@@ -123,6 +123,37 @@ def synth_clip(seed):
     return x_t, fea, cond
 
 
+def synth_state_dict():
+    """Deterministic synthetic weights of the reference architecture (oracle/weights.py over the committed 900-key schema):
+    the same state_dict feeds the CUDA arm and the CPU arm, and building it does not touch the product package."""
+    from oracle import weights as W
+    with open(os.path.join(ROOT, "tests", "golden", "state_dict_schema.json")) as f:
+        schema = [(n, tuple(sh)) for n, sh in json.load(f)["entries"]]
+    return W.synth_state_dict(schema)
+
+
+def cpu_cfg1_run(state_dict, steps=5, warmup=3):
+    """BASELINE configs[0] (16 frames, 32x32 latent) on the host cores, NOT extrapolated:
+    3 warm-ups + 5 timed forwards of the oracle port, median."""
+    from oracle import unet_oracle as O
+    from oracle import weights as W
+    cores = host_threads()
+    torch.set_num_threads(cores)
+    x_t, fea, cond = W.synth_inputs("cfg1", 16, 32, 32)
+    x = torch.cat([x_t, fea.unsqueeze(2).expand(-1, -1, 16, -1, -1)], dim=1).contiguous()
+    t = torch.full((1,), 500, dtype=torch.long)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.unet_forward(state_dict, O.UnetCfg(), x, t, cond)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    sec = statistics.median(times)
+    return {"workload": "configs[0]: 16 frames, 32x32 latent, one UNet forward", "s_per_step": sec, "steps_per_s": 1.0 / sec,
+            "cores": cores, "kind": "port", "timed": steps, "warmup": warmup}
+
+
 def cpu_baseline_run(state_dict, steps, warmup):
     """The reference's algorithm on the host cores: oracle port (the reference itself is Python and does not
     travel to this box).  Bounded sample: the first CPU_SAMPLE_FRAMES frames of the same 64x64-latent workload;
@@ -164,12 +195,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    warmup = max(args.warmup, 3)
 
-    from dawn_pytorch_b200 import DynamicNfUnet3D
-    torch.manual_seed(0)
-    net = DynamicNfUnet3D(**CTOR).eval()          # random-init weights of the reference architecture
-    sd_cpu = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    sd_cpu = synth_state_dict()                   # synthetic weights of the reference architecture (no checkpoint is reachable offline)
     config = {"workload": "configs[2]: 256x256 video = 64x64 latent, 200 frames, windowed (+-40) temporal attention, 1 UNet forward per step",
               "frames": F_CLIP * (1 if (args.gpus == 1 or args.replicas) else args.gpus), "latent": [H_LAT, W_LAT],
               "parallelism": ("single GPU" if args.gpus == 1 else
@@ -180,15 +208,18 @@ def main():
 
     if args.cpu_baseline_worker:
         cb, _ = cpu_baseline_run(sd_cpu, 3, 1)
+        cb["cfg1"] = cpu_cfg1_run(sd_cpu)
         print(json.dumps(cb))
         return
     if args.impl == "reference":
+        # the reference's algorithm on the host cores (oracle port; the product package is never imported on this arm)
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 5))
-        cb, sec = cpu_baseline_run(sd_cpu, steps, min(warmup, 1))
+        steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 5))
+        cb, sec = cpu_baseline_run(sd_cpu, steps, warmup)
+        cb["cfg1"] = cpu_cfg1_run(sd_cpu)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "steps/s", "n_gpus": args.gpus,
-                "steps": steps, "warmup": min(warmup, 1), "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True,
+                "steps": steps, "warmup": warmup, "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -197,6 +228,9 @@ def main():
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    from dawn_pytorch_b200 import DynamicNfUnet3D
+    net = DynamicNfUnet3D(**CTOR).eval()
+    net.load_state_dict(sd_cpu, strict=True)
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -275,6 +309,26 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---------------- BASELINE configs[0] (16 frames, 32x32 latent), device-resident, for the un-extrapolated CPU comparison
+    cfg1_gpu = None
+    if world == 1:
+        from oracle import weights as W
+        x1, f1, c1 = W.synth_inputs("cfg1", 16, 32, 32)
+        net.update_num_frames(16)
+        net.set_clip_invariants(f1[0].to(dev), c1[0].to(dev))
+        x1d, o1d = x1[0].to(dev), torch.empty((3, 16, 32, 32), device=dev)
+        for _ in range(5):
+            net.forward_x3(x1d, t_d, o1d)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            net.forward_x3(x1d, t_d, o1d)
+        e1.record()
+        torch.cuda.synchronize()
+        cfg1_gpu = {"workload": "configs[0]: 16 frames, 32x32 latent, one UNet forward (device-resident)",
+                    "ms_per_step": e0.elapsed_time(e1) / 20, "steps_per_s": 20e3 / e0.elapsed_time(e1), "timed": 20, "warmup": 5}
+        log(f"cfg1 on the GPU: {cfg1_gpu['ms_per_step']:.3f} ms/step")
+
     # ---------------- roofline of the dominant kernel, live CUDA-event times (category timers inside the library)
     pk = peaks()
     total_kernel_ms = sum(v["ms"] for v in prof.values())
@@ -303,9 +357,9 @@ def main():
                   "fp32-level parity, so the attainable fraction of the bf16 peak is 1/3")
     # the kernel with the largest share of the step: fused per-pixel temporal attention at level 0 (4096 px x 200 f x 64 ch)
     roofline = tensor_view("temporal_fused_l0",
-                           "temporal_fused_kernel @ level 0 (LayerNorm + QKV projection + rotary + banded softmax attention + out-projection "
-                           "+ residual per pixel sequence; mma.sync m16n8k16 FP16x3)",
-                           split_note + "; legacy mma.sync pipe (ncu: 39 % tensor-pipe active), flops = QKV 80.5 + attention 61 + out-proj 26.8 GFLOP per launch")
+                           "temporal_tc_kernel @ level 0 (LayerNorm + QKV projection + rotary + banded softmax attention + out-projection "
+                           "+ residual per pixel sequence; tcgen05 kind::f16 FP16x3, TMEM accumulators, P from TMEM)",
+                           split_note + "; flops = QKV 80.5 + attention 61 + out-proj 26.8 GFLOP per launch")
     # second view: the tcgen05 halo-tile 3x3 conv (64 -> 64 channels, 819 200 px), the largest tcgen05 kernel
     roofline_conv3 = tensor_view("conv3x3_l0", "tc_conv3_kernel<64> @ level 0 (halo-tile tcgen05 3x3 conv 64->64 ch, FP16x3 kind::f16, TMEM accumulators)",
                                  split_note)
@@ -335,7 +389,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config, "roofline": roofline, "roofline_conv3_view": roofline_conv3, "roofline_hbm_view": roofline_hbm, "step_roofline": step_roof, "cpu_baseline": cpu_baseline,
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "breakdown": breakdown}
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "cfg1": cfg1_gpu, "breakdown": breakdown}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
