@@ -32,6 +32,10 @@ def test_eps_matches_reference_golden(case):
     r = G.over_tol(out, ref)
     print(f"{case}: max|d|/(atol+rtol|ref|) = {r:.3f}, max|d| = {(out - ref).abs().max():.3e}")
     assert r <= 1.0
+    if case == "band":      # the windowed twin of the reference (`_local_opt` + local_attention.py LA:275-342) on the same clip
+        r_ul = G.over_tol(out, torch.from_numpy(G.golden(case)["eps_local_opt"]))
+        print(f"band vs the reference's _local_opt UNet: {r_ul:.3f} x tol")
+        assert r_ul <= 1.0
 
 
 def test_every_submodule_boundary_matches_oracle():

@@ -48,8 +48,10 @@ def sampler_case(net, rank, world, dev, graph_modes):
             D1.update_num_frames(Fg)
             one = D1.ddim_sample(fea.to(dev), (1, 3, Fg, h, w), cond=cond.to(dev), pairs=pairs,
                                  noise_fn=lambda k, shp: noise_global(k).reshape(shp).clone())[0].cpu()
-            print(f"[ddim] F={Fg} sharded x{world} sampler ({'graph' if use_graph else 'eager'}), 3 steps: max|d| vs single-GPU {(full - one).abs().max():.2e}",
+            dmax = (full - one).abs().max().item()
+            print(f"[ddim] F={Fg} sharded x{world} sampler ({'graph' if use_graph else 'eager'}), 3 steps: max|d| vs single-GPU {dmax:.2e}",
                   flush=True)
+            assert dmax < 2e-4, "sharded sampler disagrees with the single-GPU sampler"
             del D1, net1
         dist.barrier()
     # default noise: one clip-wide stream, sliced per rank
@@ -90,7 +92,9 @@ def main():
         if rank == 0:
             if has_golden:
                 ref = torch.from_numpy(G.golden(name)["eps"])
-                print(f"[{name}] sharded x{world} vs reference golden: over_tol {G.over_tol(full, ref):.3f}", flush=True)
+                r = G.over_tol(full, ref)
+                print(f"[{name}] sharded x{world} vs reference golden: over_tol {r:.3f}", flush=True)
+                assert r <= 1.0, "sharded forward disagrees with the reference golden"
             # unsharded run of the whole clip on rank 0 with a second module instance
             net1 = DynamicNfUnet3D(**G.CTOR).eval()
             net1.load_state_dict(G.synth_sd(), strict=True)
@@ -99,8 +103,10 @@ def main():
             net1.set_clip_invariants(fea[0].to(dev), cond[0].to(dev))
             one = net1.forward_x3(x_t[0].to(dev), tt)
             torch.cuda.synchronize()
-            print(f"[{name}] F={Fg} {h}x{w}: sharded x{world} vs single-GPU CUDA: over_tol {G.over_tol(full, one.cpu()[None]):.4f}"
+            r1 = G.over_tol(full, one.cpu()[None])
+            print(f"[{name}] F={Fg} {h}x{w}: sharded x{world} vs single-GPU CUDA: over_tol {r1:.4f}"
                   f"  max|d| {(full[0] - one.cpu()).abs().max():.2e};  sharded step {ms:.2f} ms", flush=True)
+            assert r1 <= 0.25, "sharded forward disagrees with the single-GPU forward"
             del net1
         dist.barrier()
     modes = ([False] if "ddim" in what else []) + ([True] if "ddim_graph" in what else [])
