@@ -36,8 +36,8 @@ using namespace tc;
 constexpr int WMAX = kTtcWindowMax;
 constexpr int SN = 160;                    // key columns of an S tile
 constexpr int CW = 128;                    // columns one softmax thread looks at (32 rows + 2*band <= 112, + 16 alignment)
-constexpr int NTH = 320;
-constexpr int MMA_WARP = 8, LOAD_WARP = 9;
+constexpr int NTH = 384;                   // 8 compute warps + one auxiliary warpgroup (issuers in warps 8, 9)
+constexpr int MMA_WARP = 8;             // warps 8, 9: MMA issuers of tile 0 / tile 1
 constexpr float LOG2E = 1.4426950408889634f;
 
 // shared-memory map (bytes from a 1024-aligned base); every UMMA operand starts on a 1024-byte swizzle atom
@@ -125,20 +125,22 @@ __device__ __forceinline__ void store_row_chunk(uint8_t* base, int row, int c8, 
 }
 
 struct Bars {
-  uint64_t x_ready, wq_ready, wq_free, wo_ready, wo_free, kv_ready;
+  uint64_t x_ready, wq_ready, wq_free, wo_ready, wo_free, kv_ready, v_ready;
   uint64_t proj_ready[2], s_ready[2], p_ready[2], o_ready[2], oh_ready[2], y_ready[2];
 };
 
+template <bool TRACE>
 __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArgs a) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ Bars bars;
   __shared__ uint32_t s_tmem_base;
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // round up inside the shared window (pointer arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    mbar_init(&bars.x_ready, 256); mbar_init(&bars.kv_ready, 256);
-    mbar_init(&bars.wq_ready, 1); mbar_init(&bars.wq_free, 1); mbar_init(&bars.wo_ready, 1); mbar_init(&bars.wo_free, 1);
+    mbar_init(&bars.x_ready, 256); mbar_init(&bars.kv_ready, 256); mbar_init(&bars.v_ready, 256);
+    mbar_init(&bars.wq_ready, 1); mbar_init(&bars.wq_free, 2); mbar_init(&bars.wo_ready, 1); mbar_init(&bars.wo_free, 2);
     for (int j = 0; j < 2; ++j) {
       mbar_init(&bars.proj_ready[j], 1); mbar_init(&bars.s_ready[j], 1); mbar_init(&bars.o_ready[j], 1); mbar_init(&bars.y_ready[j], 1);
       mbar_init(&bars.p_ready[j], 128); mbar_init(&bars.oh_ready[j], 128);
@@ -167,7 +169,10 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
   const int nunits = a.P * a.nseg;
   const int band = a.band;
 
+  // Registers are per scheduler partition (16K each, 3 warps per partition here: launch at 168 per thread).  The auxiliary
+  // warpgroup hands most of its share to the two compute warps of its partition: 2 x 216 + 72 <= 512.
   if (warp < 8) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
     // ======================================================================= compute warpgroups
     const int j = warp >> 2;                               // tile owned by this warpgroup
     const int wq = warp & 3;                               // TMEM lane quarter
@@ -177,49 +182,62 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
     float* tb = reinterpret_cast<float*>(smem + TBL_OFF) + j * kTtcTable;
     const float2* s_stat = reinterpret_cast<const float2*>(smem + ST_OFF);
     const float* ws = reinterpret_cast<const float*>(smem + WS_OFF);
-    uint32_t it = 0, ui = 0;                               // head iterations / units done by this CTA
-    uint32_t nact[2] = {0, 0}, nq[2] = {0, 0};             // completed phases of the per-tile barriers (rows exist / queries exist)
-    const bool tr = (a.trace != nullptr) && blockIdx.x == 0 && wgtid == 0;   // cycle trace of CTA 0 (one thread per warpgroup)
+    uint32_t ui = 0;                                       // units done by this CTA
+    // completed phases of the per-tile barriers (rows exist / queries exist), for this warpgroup's tile and for the other one
+    uint32_t nact_own = 0, nact_oth = 0, nq_own = 0, nq_oth = 0;
+    uint64_t* const proj_own = &bars.proj_ready[j];
+    uint64_t* const proj_oth = &bars.proj_ready[1 - j];
+    uint64_t* const o_oth = &bars.o_ready[1 - j];
+    const bool tr = TRACE && (a.trace != nullptr) && blockIdx.x == 0 && wgtid == 0;   // cycle trace of CTA 0 (one thread per warpgroup)
     long long tc_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0;
-#define TTC_T(i) do { if (tr) { const long long t1_ = clock64(); tc_[i] += t1_ - t0; t0 = t1_; } } while (0)
+#define TTC_T(i) do { if (TRACE && tr) { const long long t1_ = clock64(); tc_[i] += t1_ - t0; t0 = t1_; } } while (0)
 
     for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ui) {
       const int pix = u / a.nseg;
       const TtcSegment sg = a.seg[u - pix * a.nseg];
       TtcTile tl[2];
       ttc_tiles(sg, band, tl);
-      const bool act[2] = {tl[0].r1 > tl[0].r0, tl[1].r1 > tl[1].r0};
-      const bool hq[2] = {tl[0].q1 > tl[0].q0, tl[1].q1 > tl[1].q0};
-      const TtcTile T = tl[j];
+      const TtcTile T = j ? tl[1] : tl[0], To = j ? tl[0] : tl[1];
+      const bool act_own = T.r1 > T.r0, act_oth = To.r1 > To.r0, hq_own = T.q1 > T.q0, hq_oth = To.q1 > To.q0;
       const int row = T.r0 + l;                            // window row of this thread
       const bool row_ok = row < T.r1;
       const bool dbg = (a.dbg != nullptr) && u == 0;
 
       if (tr) t0 = clock64();
       // ------------------------------------------------------------------ prologue: x rows -> LN statistics + fp16 split
+      // 16 lanes x float4 = one 64-channel row, 16 rows per pass; all loads of a half (7 passes) are in flight together
       {
-        const int l16 = tid & 15, rg = tid >> 4;           // 16 lanes x float4 = one 64-channel row; 16 rows per pass
+        const int l16 = tid & 15, rg = tid >> 4;
         float2* st = reinterpret_cast<float2*>(smem + ST_OFF);
-#pragma unroll 2
-        for (int r0 = 0; r0 < sg.wn; r0 += 16) {
-          const int r = r0 + rg;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r < sg.wn) v = __ldg(reinterpret_cast<const float4*>(a.x + ((size_t)(sg.w0 + r) * a.P + pix) * a.ldx) + l16);
-          float s = (v.x + v.y) + (v.z + v.w);
+        const float* xb = a.x + ((size_t)sg.w0 * a.P + pix) * a.ldx + 4 * l16;
+        const size_t fstride = (size_t)a.P * a.ldx;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          float4 v[7];
 #pragma unroll
-          for (int o = 1; o < 16; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          const float mu = s * (1.0f / 64.f);
-          const float d0 = v.x - mu, d1 = v.y - mu, d2 = v.z - mu, d3 = v.w - mu;
-          float ss = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+          for (int i = 0; i < 7; ++i) {
+            const int r = (half * 7 + i) * 16 + rg;
+            v[i] = (r < sg.wn) ? __ldg(reinterpret_cast<const float4*>(xb + (size_t)r * fstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
-          for (int o = 1; o < 16; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-          if (r < sg.wn) {
-            if (l16 == 0) st[r] = make_float2(mu, 1.0f / sqrtf(ss * (1.0f / 64.f) + 1e-5f));
-            uint32_t h0, l0, h1, l1;
-            split_f16x2(v.x, v.y, h0, l0); split_f16x2(v.z, v.w, h1, l1);
-            const uint32_t off = swz(r, l16 >> 1) + (l16 & 1) * 8;
-            *reinterpret_cast<uint2*>(smem + XH_OFF + off) = make_uint2(h0, h1);
-            *reinterpret_cast<uint2*>(smem + XL_OFF + off) = make_uint2(l0, l1);
+          for (int i = 0; i < 7; ++i) {
+            const int r = (half * 7 + i) * 16 + rg;
+            float s = (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mu = s * (1.0f / 64.f);
+            const float d0 = v[i].x - mu, d1 = v[i].y - mu, d2 = v[i].z - mu, d3 = v[i].w - mu;
+            float ss = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            if (r < sg.wn) {
+              if (l16 == 0) st[r] = make_float2(mu, 1.0f / sqrtf(ss * (1.0f / 64.f) + 1e-5f));
+              uint32_t h0, l0, h1, l1;
+              split_f16x2(v[i].x, v[i].y, h0, l0); split_f16x2(v[i].z, v[i].w, h1, l1);
+              const uint32_t off = swz(r, l16 >> 1) + (l16 & 1) * 8;
+              *reinterpret_cast<uint2*>(smem + XH_OFF + off) = make_uint2(h0, h1);
+              *reinterpret_cast<uint2*>(smem + XL_OFF + off) = make_uint2(l0, l1);
+            }
           }
         }
         fence_proxy_async();
@@ -230,17 +248,21 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
       TTC_T(0);
       const float2 stat = row_ok ? s_stat[row] : make_float2(0.f, 1.f);
       const float fa = stat.y * a.inv_wscale, fb = -stat.y * stat.x;
-      const float* rotp = a.rot + (size_t)(sg.w0 + (row_ok ? row : T.r0)) * 32;
+      const float4* rotp = reinterpret_cast<const float4*>(a.rot + (size_t)(sg.w0 + (row_ok ? row : T.r0)) * 32);
       float inv_l = 1.f;
 
-      for (int h = 0; h < 8; ++h, ++it) {
-        // table of this head for the softmax of this warpgroup (previous head's readers are done: they arrived on p_ready before
-        // anyone could pass o_ready)
-        if (hq[j]) *reinterpret_cast<float4*>(tb + 4 * wgtid) = __ldg(reinterpret_cast<const float4*>(a.table + h * kTtcTable) + wgtid);
+      for (int h = 0; h < 8; ++h) {
+        // prefetch what this head needs from global memory before blocking on the projection: the (cos, sin) row of this thread's
+        // frame (the shared-memory carve-out leaves ~9 KB of L1: these come from L2) and this thread's slice of the bias/mask table
+        float4 cs4[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cs4[i] = __ldg(rotp + i);
+        float4 tab4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (hq_own) tab4 = __ldg(reinterpret_cast<const float4*>(a.table + h * kTtcTable) + wgtid);
 
         // -------------------------------------------------------------- E1: projection accumulator -> Q_h, K_h, V_h^T
-        if (act[j]) {
-          mbar_wait(&bars.proj_ready[j], nact[j] & 1);
+        if (act_own) {
+          mbar_wait(proj_own, nact_own & 1);
           TTC_T(1);
           tc_fence_after();
           uint32_t rq[32], rk[32], rv[32];
@@ -248,7 +270,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
           tmem_ld32_async(ta, rq); tmem_ld32_async(ta + 32, rk); tmem_ld32_async(ta + 64, rv);
           tmem_wait_ld();
           // K/V/Q of the previous head may still be read by the other tile's S / PV
-          if (nq[1 - j] > 0) mbar_wait(&bars.o_ready[1 - j], (nq[1 - j] - 1) & 1);
+          if (nq_oth > 0) mbar_wait(o_oth, (nq_oth - 1) & 1);
           TTC_T(2);
           if (dbg && h == 0 && row_ok) {
             float* d = a.dbg + (size_t)row * 96;
@@ -261,8 +283,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
               float q8[8], k8[8];
-              const float4 cs0 = __ldg(reinterpret_cast<const float4*>(rotp) + 2 * c8);        // (cos, sin) of pairs 4 c8, 4 c8 + 1
-              const float4 cs1 = __ldg(reinterpret_cast<const float4*>(rotp) + 2 * c8 + 1);    // pairs 4 c8 + 2, 4 c8 + 3
+              const float4 cs0 = cs4[2 * c8], cs1 = cs4[2 * c8 + 1];      // (cos, sin) of pairs 4 c8 .. 4 c8 + 3
               const float cs[8] = {cs0.x, cs0.y, cs0.z, cs0.w, cs1.x, cs1.y, cs1.z, cs1.w};
 #pragma unroll
               for (int pp = 0; pp < 4; ++pp) {
@@ -278,6 +299,12 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
               store_row_chunk(smem + Q_OFF, row, c8, q8);
               store_row_chunk(smem + K_OFF, row, c8, k8);
             }
+          }
+          // K_h and Q_h are complete: S = Q K^T starts while V_h^T is still being written
+          fence_proxy_async();
+          mbar_arrive(&bars.kv_ready);
+          if (row_ok) {
+            const float* wsq = ws + h * 32;
             // V_h^T: element (dim d, key = row) of chunk row >> 6
             uint8_t* vh = smem + VH_OFF + (row >> 6) * 4096 + (row & 7) * 2;
             uint8_t* vl = smem + VL_OFF + (row >> 6) * 4096 + (row & 7) * 2;
@@ -294,18 +321,20 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
           }
           tc_fence_before();
           fence_proxy_async();
-          ++nact[j];
-        } else if (nq[1 - j] > 0) {
-          // nothing to write, but keep the ordering argument simple: no early arrival before the other tile's reads are done
-          mbar_wait(&bars.o_ready[1 - j], (nq[1 - j] - 1) & 1);
+          ++nact_own;
+        } else {
+          if (nq_oth > 0) mbar_wait(o_oth, (nq_oth - 1) & 1);
+          mbar_arrive(&bars.kv_ready);
         }
-        mbar_arrive(&bars.kv_ready);
+        mbar_arrive(&bars.v_ready);
         TTC_T(3);
 
-        if (hq[j]) {
-          named_bar(1 + j, 128);                                   // table staged by all 128 threads of this warpgroup
+        if (hq_own) {
+          // table of this head (the previous head's readers are done: they arrived on p_ready before anyone could pass o_ready)
+          *reinterpret_cast<float4*>(tb + 4 * wgtid) = tab4;
+          named_bar(1 + j, 128);
           // ------------------------------------------------------------ E2: softmax of this thread's row
-          mbar_wait(&bars.s_ready[j], nq[j] & 1);
+          mbar_wait(&bars.s_ready[j], nq_own & 1);
           TTC_T(4);
           tc_fence_after();
           int xw = T.r0 + 32 * wq - band - T.kb;
@@ -368,7 +397,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
           TTC_T(5);
 
           // ------------------------------------------------------------ E3: O / rowsum -> O_h
-          mbar_wait(&bars.o_ready[j], nq[j] & 1);
+          mbar_wait(&bars.o_ready[j], nq_own & 1);
           TTC_T(6);
           tc_fence_after();
           {
@@ -395,17 +424,23 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
           fence_proxy_async();
           mbar_arrive(&bars.oh_ready[j]);
           TTC_T(7);
-          ++nq[j];
+          ++nq_own;
         }
-        if (hq[1 - j]) ++nq[1 - j];
-        if (act[1 - j]) ++nact[1 - j];
+        if (hq_oth) ++nq_oth;
+        if (act_oth) ++nact_oth;
       }
       // the next prologue overwrites X: the other tile's last projection must have finished reading it
-      if (act[1 - j]) mbar_wait(&bars.proj_ready[1 - j], (nact[1 - j] - 1) & 1);
+      if (act_oth) mbar_wait(proj_oth, (nact_oth - 1) & 1);
 
       // ------------------------------------------------------------------ unit epilogue: out = residual + Y
-      if (hq[j]) {
-        mbar_wait(&bars.y_ready[j], (nq[j] / 8 - 1) & 1);        // y_ready completes once per unit with queries
+      if (hq_own) {
+        const bool is_q = row >= T.q0 && row < T.q1;
+        const size_t orow = (size_t)(sg.w0 + (is_q ? row : T.q0) - a.q_lo) * a.P + pix;
+        const float4* rp = reinterpret_cast<const float4*>(a.res + orow * a.ldr);
+        float4 rr[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rr[i] = rp[i];                 // residual row in flight while the last Y finishes
+        mbar_wait(&bars.y_ready[j], (nq_own / 8 - 1) & 1);        // y_ready completes once per unit with queries
         TTC_T(8);
         tc_fence_after();
         uint32_t ry[64];
@@ -415,15 +450,12 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
           tmem_ld32_async(tmem_base + lane_addr + y_col(j) + 32, ry2[1]);
           tmem_wait_ld();
         }
-        if (row >= T.q0 && row < T.q1) {
-          const size_t orow = (size_t)(sg.w0 + row - a.q_lo) * a.P + pix;
-          const float4* rp = reinterpret_cast<const float4*>(a.res + orow * a.ldr);
+        if (is_q) {
           float4* op = reinterpret_cast<float4*>(a.out + orow * a.ldo);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float4 r = rp[i];
-            op[i] = make_float4(fmaf(__uint_as_float(ry[4 * i]), a.inv_oscale, r.x), fmaf(__uint_as_float(ry[4 * i + 1]), a.inv_oscale, r.y),
-                                fmaf(__uint_as_float(ry[4 * i + 2]), a.inv_oscale, r.z), fmaf(__uint_as_float(ry[4 * i + 3]), a.inv_oscale, r.w));
+            op[i] = make_float4(fmaf(__uint_as_float(ry[4 * i]), a.inv_oscale, rr[i].x), fmaf(__uint_as_float(ry[4 * i + 1]), a.inv_oscale, rr[i].y),
+                                fmaf(__uint_as_float(ry[4 * i + 2]), a.inv_oscale, rr[i].z), fmaf(__uint_as_float(ry[4 * i + 3]), a.inv_oscale, rr[i].w));
           }
         }
         tc_fence_before();
@@ -431,54 +463,60 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
       }
     }
     if (tr) for (int i = 0; i < 12; ++i) a.trace[16 * j + i] = (unsigned long long)tc_[i];
-  } else if (warp == LOAD_WARP) {
-    // ======================================================================= weight loader
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
+  }
+  if (warp == MMA_WARP || warp == MMA_WARP + 1) {
+    // ======================================================================= MMA issuers: warp 8 lane 0 -> tile 0 (+ weight images), warp 9 lane 0 -> tile 1
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
-        for (int h = 0; h < 8; ++h, ++it) {
-          mbar_wait(&bars.wq_free, (it & 1) ^ 1);
-          mbar_arrive_expect_tx(&bars.wq_ready, WQ_BYTES);
-          bulk_copy_g2s(smem + WQ_OFF, a.Wqkv + (size_t)h * WQ_BYTES, WQ_BYTES, &bars.wq_ready);
-          mbar_wait(&bars.wo_free, (it & 1) ^ 1);
-          mbar_arrive_expect_tx(&bars.wo_ready, WO_BYTES);
-          bulk_copy_g2s(smem + WO_OFF, a.Wout + (size_t)h * WO_BYTES, WO_BYTES, &bars.wo_ready);
-        }
-      }
-    }
-  } else if (warp == MMA_WARP) {
-    // ======================================================================= MMA issuer
-    if (lane == 0) {
+      const int j = warp - MMA_WARP;
       const uint32_t sb = smem_u32(smem);
-      uint32_t it = 0, ui = 0, nq[2] = {0, 0};
-      const bool tr = (a.trace != nullptr) && blockIdx.x == 0;
+      uint32_t it = 0, ui = 0, nqj = 0;
+      const bool tr = TRACE && (a.trace != nullptr) && blockIdx.x == 0;
       long long tc_[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0;
       const long long t_begin = clock64();
       constexpr uint32_t ID96 = idesc_n(96), ID160 = idesc_n(SN), ID32 = idesc_n(32), ID64 = idesc_n(64);
+      const uint32_t my_units = (nunits - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const uint32_t total_it = my_units * 8;
+      // weight images (tile 0's issuer): a buffer is refilled as soon as BOTH issuers have committed its last readers
+      auto load_wq = [&](uint32_t itn) {
+        if (j != 0 || itn >= total_it) return;
+        mbar_wait(&bars.wq_free, (itn & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars.wq_ready, WQ_BYTES);
+        bulk_copy_g2s(smem + WQ_OFF, a.Wqkv + (size_t)(itn & 7) * WQ_BYTES, WQ_BYTES, &bars.wq_ready);
+      };
+      auto load_wo = [&](uint32_t itn) {
+        if (j != 0 || itn >= total_it) return;
+        mbar_wait(&bars.wo_free, (itn & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars.wo_ready, WO_BYTES);
+        bulk_copy_g2s(smem + WO_OFF, a.Wout + (size_t)(itn & 7) * WO_BYTES, WO_BYTES, &bars.wo_ready);
+      };
+      load_wq(0); load_wo(0);
       for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ui) {
         const int pix = u / a.nseg;
         const TtcSegment sg = a.seg[u - pix * a.nseg];
         TtcTile tl[2];
         ttc_tiles(sg, band, tl);
-        const bool act[2] = {tl[0].r1 > tl[0].r0, tl[1].r1 > tl[1].r0};
-        const bool hq[2] = {tl[0].q1 > tl[0].q0, tl[1].q1 > tl[1].q0};
+        const TtcTile T = j ? tl[1] : tl[0];
+        const bool act = T.r1 > T.r0, hq = T.q1 > T.q0;
+        const uint32_t ro = (uint32_t)(T.r0 >> 3) * 1024u, ko = (uint32_t)(T.kb >> 3) * 1024u;
+        const uint64_t x_hi = make_desc(sb + XH_OFF + ro), x_lo = make_desc(sb + XL_OFF + ro);
+        const uint64_t w_hi = make_desc(sb + WQ_OFF), w_lo = make_desc(sb + WQ_OFF + 96 * 128);
+        const uint64_t qd = make_desc(sb + Q_OFF + ro), kd = make_desc(sb + K_OFF + ko);
+        const uint64_t od = make_desc(sb + O_OFF + ro), wd = make_desc(sb + WO_OFF);
+        const uint32_t d_s = tmem_base + s_col(j), d_o = tmem_base + o_col(j), d_y = tmem_base + y_col(j);
 
         auto issue_proj = [&](uint32_t itn) {
           mbar_wait(&bars.wq_ready, itn & 1);
           TTC_T(1);
           tc_fence_after();
-          for (int j = 0; j < 2; ++j) {
-            if (!act[j]) continue;
-            const uint32_t ro = (uint32_t)(tl[j].r0 >> 3) * 1024u;
-            const uint64_t ahi = make_desc(sb + XH_OFF + ro), alo = make_desc(sb + XL_OFF + ro);
-            const uint64_t bhi = make_desc(sb + WQ_OFF), blo = make_desc(sb + WQ_OFF + 96 * 128);
-            const uint32_t d = tmem_base + s_col(j);
+          if (act) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint64_t o = (uint64_t)(2 * ks);
-              tc_mma_f16(d, alo + o, bhi + o, ID96, ks ? 1u : 0u);
-              tc_mma_f16(d, ahi + o, blo + o, ID96, 1u);
-              tc_mma_f16(d, ahi + o, bhi + o, ID96, 1u);
+              tc_mma_f16(d_s, x_lo + o, w_hi + o, ID96, ks ? 1u : 0u);
+              tc_mma_f16(d_s, x_hi + o, w_lo + o, ID96, 1u);
+              tc_mma_f16(d_s, x_hi + o, w_hi + o, ID96, 1u);
             }
             tc_commit(&bars.proj_ready[j]);
           }
@@ -492,39 +530,35 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
         fence_proxy_async();
         issue_proj(it);
         for (int h = 0; h < 8; ++h, ++it) {
+          load_wq(it + 1);                                 // both issuers have committed this head's projections by the time kv_ready can complete
           mbar_wait(&bars.kv_ready, it & 1);
           TTC_T(3);
           fence_proxy_async();
           tc_fence_after();
-          for (int j = 0; j < 2; ++j) {
-            if (!hq[j]) continue;
-            const uint64_t qd = make_desc(sb + Q_OFF + (uint32_t)(tl[j].r0 >> 3) * 1024u);
-            const uint64_t kd = make_desc(sb + K_OFF + (uint32_t)(tl[j].kb >> 3) * 1024u);
-            const uint32_t d = tmem_base + s_col(j);
+          if (hq) {
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
               const uint64_t hi = (uint64_t)(2 * ks), lo = (uint64_t)(4 + 2 * ks);
-              tc_mma_f16(d, qd + lo, kd + hi, ID160, ks ? 1u : 0u);
-              tc_mma_f16(d, qd + hi, kd + lo, ID160, 1u);
-              tc_mma_f16(d, qd + hi, kd + hi, ID160, 1u);
+              tc_mma_f16(d_s, qd + lo, kd + hi, ID160, ks ? 1u : 0u);
+              tc_mma_f16(d_s, qd + hi, kd + lo, ID160, 1u);
+              tc_mma_f16(d_s, qd + hi, kd + hi, ID160, 1u);
             }
             tc_commit(&bars.s_ready[j]);
-          }
-          TTC_T(4);
-          for (int j = 0; j < 2; ++j) {
-            if (!hq[j]) continue;
-            mbar_wait(&bars.p_ready[j], nq[j] & 1);
-            TTC_T(5 + j);
+            TTC_T(4);
+            mbar_wait(&bars.p_ready[j], nqj & 1);
+            mbar_wait(&bars.v_ready, it & 1);
+            TTC_T(5);
+            fence_proxy_async();
             tc_fence_after();
-            const uint32_t pa = tmem_base + s_col(j), d = tmem_base + o_col(j);
 #pragma unroll
             for (int s = 0; s < SN / 16; ++s) {
-              const int key = tl[j].kb + 16 * s;
-              const uint32_t vo = (uint32_t)(key >> 6) * 4096u + (uint32_t)(key & 63) * 2u;
+              // keys kb + 16 s ..: chunk (kb + 16 s) >> 6, 32-byte step inside the chunk
+              const uint32_t key = (uint32_t)T.kb + 16u * s;
+              const uint32_t vo = (key >> 6) * 4096u + (key & 63u) * 2u;
               const uint64_t vh = make_desc(sb + VH_OFF + vo), vl = make_desc(sb + VL_OFF + vo);
-              tc_mma_f16_ts(d, pa + 80 + 8 * s, vh, ID32, s ? 1u : 0u);
-              tc_mma_f16_ts(d, pa + 8 * s, vl, ID32, 1u);
-              tc_mma_f16_ts(d, pa + 8 * s, vh, ID32, 1u);
+              tc_mma_f16_ts(d_o, d_s + 80 + 8 * s, vh, ID32, s ? 1u : 0u);
+              tc_mma_f16_ts(d_o, d_s + 8 * s, vl, ID32, 1u);
+              tc_mma_f16_ts(d_o, d_s + 8 * s, vh, ID32, 1u);
             }
             tc_commit(&bars.o_ready[j]);
             TTC_T(7);
@@ -533,30 +567,27 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
           if (h < 7) issue_proj(it + 1);
           mbar_wait(&bars.wo_ready, it & 1);
           TTC_T(8);
-          for (int j = 0; j < 2; ++j) {
-            if (!hq[j]) continue;
-            mbar_wait(&bars.oh_ready[j], nq[j] & 1);
-            TTC_T(9 + j);
+          if (hq) {
+            mbar_wait(&bars.oh_ready[j], nqj & 1);
+            TTC_T(9);
             fence_proxy_async();
             tc_fence_after();
-            const uint64_t od = make_desc(sb + O_OFF + (uint32_t)(tl[j].r0 >> 3) * 1024u);
-            const uint64_t wd = make_desc(sb + WO_OFF);
-            const uint32_t d = tmem_base + y_col(j);
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
               const uint64_t hi = (uint64_t)(2 * ks), lo = (uint64_t)(4 + 2 * ks);
-              tc_mma_f16(d, od + lo, wd + hi, ID64, (h || ks) ? 1u : 0u);
-              tc_mma_f16(d, od + hi, wd + lo, ID64, 1u);
-              tc_mma_f16(d, od + hi, wd + hi, ID64, 1u);
+              tc_mma_f16(d_y, od + lo, wd + hi, ID64, (h || ks) ? 1u : 0u);
+              tc_mma_f16(d_y, od + hi, wd + lo, ID64, 1u);
+              tc_mma_f16(d_y, od + hi, wd + hi, ID64, 1u);
             }
             if (h == 7) tc_commit(&bars.y_ready[j]);
-            ++nq[j];
+            ++nqj;
             TTC_T(11);
           }
           tc_commit(&bars.wo_free);
+          load_wo(it + 1);
         }
       }
-      if (tr) {
+      if (tr && j == 0) {
         for (int i = 0; i < 12; ++i) a.trace[32 + i] = (unsigned long long)tc_[i];
         a.trace[44] = (unsigned long long)(clock64() - t_begin); a.trace[45] = it;
       }
@@ -607,10 +638,12 @@ int launch_temporal_tc(const TemporalTcArgs& a_in, cudaStream_t st) {
     int dev = 0;
     DAWN_CUDA_OK(cudaGetDevice(&dev));
     DAWN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    DAWN_CUDA_OK(cudaFuncSetAttribute(temporal_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
+    DAWN_CUDA_OK(cudaFuncSetAttribute(temporal_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
+    DAWN_CUDA_OK(cudaFuncSetAttribute(temporal_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
   }
   const int grid = std::min(a.P * a.nseg, num_sms);
-  temporal_tc_kernel<<<grid, NTH, SMEM_DYN, st>>>(a);
+  if (a.trace) temporal_tc_kernel<true><<<grid, NTH, SMEM_DYN, st>>>(a);
+  else temporal_tc_kernel<false><<<grid, NTH, SMEM_DYN, st>>>(a);
   DAWN_LAUNCH_OK();
   return 0;
 }
