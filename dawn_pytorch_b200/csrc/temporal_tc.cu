@@ -74,6 +74,34 @@ __device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, 
       "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Every operand of this kernel is a K-major, 128-byte-swizzled panel: the descriptors differ only in their low word (start address
+// >> 4 | LBO << 16); the high word (SBO = 1024 B, descriptor version 1, SWIZZLE_128B) is one constant.  Keeping 32-bit low words
+// instead of 64-bit descriptors halves the issuer's (uniform-)register pressure.
+constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t blo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "r"(blo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -170,9 +198,9 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
   const int band = a.band;
 
   // Registers are per scheduler partition (16K each, 3 warps per partition here: launch at 168 per thread).  The auxiliary
-  // warpgroup hands most of its share to the two compute warps of its partition: 2 x 216 + 72 <= 512.
+  // warpgroup hands most of its share to the two compute warps of its partition: 2 x 208 + 88 = 504 = the 3 x 168 this CTA owns per partition (asking for more than the CTA's pool blocks forever).
   if (warp < 8) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory");
     // ======================================================================= compute warpgroups
     const int j = warp >> 2;                               // tile owned by this warpgroup
     const int wq = warp & 3;                               // TMEM lane quarter
@@ -192,6 +220,8 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
     long long tc_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0;
 #define TTC_T(i) do { if (TRACE && tr) { const long long t1_ = clock64(); tc_[i] += t1_ - t0; t0 = t1_; } } while (0)
 
+    float4 xpre[7];                                        // this thread's share of the next window's first 112 x rows, requested one unit ahead
+    bool have_pre = false;
     for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ui) {
       const int pix = u / a.nseg;
       const TtcSegment sg = a.seg[u - pix * a.nseg];
@@ -205,39 +235,45 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
 
       if (tr) t0 = clock64();
       // ------------------------------------------------------------------ prologue: x rows -> LN statistics + fp16 split
-      // 16 lanes x float4 = one 64-channel row, 16 rows per pass; all loads of a half (7 passes) are in flight together
+      // 16 lanes x float4 = one 64-channel row, 16 rows per pass.  The rows were requested during the previous unit's last head
+      // (xpre holds them); only the first unit of a CTA loads here.
       {
         const int l16 = tid & 15, rg = tid >> 4;
         float2* st = reinterpret_cast<float2*>(smem + ST_OFF);
         const float* xb = a.x + ((size_t)sg.w0 * a.P + pix) * a.ldx + 4 * l16;
         const size_t fstride = (size_t)a.P * a.ldx;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          float4 v[7];
+        float4 xsec[7];                                    // rows 112 + : loaded now, consumed after the prefetched half
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+          const int r = (7 + i) * 16 + rg;
+          xsec[i] = (r < sg.wn) ? __ldg(reinterpret_cast<const float4*>(xb + (size_t)r * fstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (!have_pre) {
 #pragma unroll
           for (int i = 0; i < 7; ++i) {
-            const int r = (half * 7 + i) * 16 + rg;
-            v[i] = (r < sg.wn) ? __ldg(reinterpret_cast<const float4*>(xb + (size_t)r * fstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int r = i * 16 + rg;
+            xpre[i] = (r < sg.wn) ? __ldg(reinterpret_cast<const float4*>(xb + (size_t)r * fstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+        }
 #pragma unroll
-          for (int i = 0; i < 7; ++i) {
-            const int r = (half * 7 + i) * 16 + rg;
-            float s = (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        for (int i = 0; i < 14; ++i) {
+          const int r = i * 16 + rg;
+          const float4 v = i < 7 ? xpre[i < 7 ? i : 0] : xsec[i < 7 ? 0 : i - 7];
+          float s = (v.x + v.y) + (v.z + v.w);
 #pragma unroll
-            for (int o = 1; o < 16; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            const float mu = s * (1.0f / 64.f);
-            const float d0 = v[i].x - mu, d1 = v[i].y - mu, d2 = v[i].z - mu, d3 = v[i].w - mu;
-            float ss = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+          for (int o = 1; o < 16; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          const float mu = s * (1.0f / 64.f);
+          const float d0 = v.x - mu, d1 = v.y - mu, d2 = v.z - mu, d3 = v.w - mu;
+          float ss = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
 #pragma unroll
-            for (int o = 1; o < 16; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-            if (r < sg.wn) {
-              if (l16 == 0) st[r] = make_float2(mu, 1.0f / sqrtf(ss * (1.0f / 64.f) + 1e-5f));
-              uint32_t h0, l0, h1, l1;
-              split_f16x2(v[i].x, v[i].y, h0, l0); split_f16x2(v[i].z, v[i].w, h1, l1);
-              const uint32_t off = swz(r, l16 >> 1) + (l16 & 1) * 8;
-              *reinterpret_cast<uint2*>(smem + XH_OFF + off) = make_uint2(h0, h1);
-              *reinterpret_cast<uint2*>(smem + XL_OFF + off) = make_uint2(l0, l1);
-            }
+          for (int o = 1; o < 16; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+          if (r < sg.wn) {
+            if (l16 == 0) st[r] = make_float2(mu, 1.0f / sqrtf(ss * (1.0f / 64.f) + 1e-5f));
+            uint32_t h0, l0, h1, l1;
+            split_f16x2(v.x, v.y, h0, l0); split_f16x2(v.z, v.w, h1, l1);
+            const uint32_t off = swz(r, l16 >> 1) + (l16 & 1) * 8;
+            *reinterpret_cast<uint2*>(smem + XH_OFF + off) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(smem + XL_OFF + off) = make_uint2(l0, l1);
           }
         }
         fence_proxy_async();
@@ -395,7 +431,25 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
           tc_fence_before();
           mbar_arrive(&bars.p_ready[j]);
           TTC_T(5);
-
+        }
+        if (h == 7) {
+          // request the next unit's x rows now: their DRAM latency hides behind this head's P*V, E3, Y and the epilogue
+          const int un = u + (int)gridDim.x;
+          have_pre = un < nunits;
+          if (have_pre) {
+            const int pixn = un / a.nseg;
+            const TtcSegment sn = a.seg[un - pixn * a.nseg];
+            const int l16 = tid & 15, rg = tid >> 4;
+            const float* xb = a.x + ((size_t)sn.w0 * a.P + pixn) * a.ldx + 4 * l16;
+            const size_t fstride = (size_t)a.P * a.ldx;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+              const int r = i * 16 + rg;
+              xpre[i] = (r < sn.wn) ? __ldg(reinterpret_cast<const float4*>(xb + (size_t)r * fstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        }
+        if (hq_own) {
           // ------------------------------------------------------------ E3: O / rowsum -> O_h
           mbar_wait(&bars.o_ready[j], nq_own & 1);
           TTC_T(6);
@@ -406,7 +460,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
             tmem_wait_ld();
             if (dbg && h == 0 && row_ok) {
               float* d = a.dbg + (size_t)WMAX * (96 + 130) + (size_t)row * 33;
-              d[0] = lsum;
+              d[0] = 1.0f / inv_l;
 #pragma unroll
               for (int i = 0; i < 32; ++i) d[1 + i] = __uint_as_float(ro[i]);
             }
@@ -437,25 +491,32 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
         const bool is_q = row >= T.q0 && row < T.q1;
         const size_t orow = (size_t)(sg.w0 + (is_q ? row : T.q0) - a.q_lo) * a.P + pix;
         const float4* rp = reinterpret_cast<const float4*>(a.res + orow * a.ldr);
-        float4 rr[16];
+        float4 rr[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) rr[i] = rp[i];                 // residual row in flight while the last Y finishes
-        mbar_wait(&bars.y_ready[j], (nq_own / 8 - 1) & 1);        // y_ready completes once per unit with queries
+        for (int i = 0; i < 8; ++i) rr[i] = rp[i];                  // first half of the residual row in flight while the last Y finishes
+        mbar_wait(&bars.y_ready[j], (nq_own / 8 - 1) & 1);       // y_ready completes once per unit with queries
         TTC_T(8);
         tc_fence_after();
-        uint32_t ry[64];
-        {
-          uint32_t (*ry2)[32] = reinterpret_cast<uint32_t (*)[32]>(ry);
-          tmem_ld32_async(tmem_base + lane_addr + y_col(j), ry2[0]);
-          tmem_ld32_async(tmem_base + lane_addr + y_col(j) + 32, ry2[1]);
-          tmem_wait_ld();
-        }
-        if (is_q) {
-          float4* op = reinterpret_cast<float4*>(a.out + orow * a.ldo);
+        float4* op = reinterpret_cast<float4*>(a.out + orow * a.ldo);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            op[i] = make_float4(fmaf(__uint_as_float(ry[4 * i]), a.inv_oscale, rr[i].x), fmaf(__uint_as_float(ry[4 * i + 1]), a.inv_oscale, rr[i].y),
-                                fmaf(__uint_as_float(ry[4 * i + 2]), a.inv_oscale, rr[i].z), fmaf(__uint_as_float(ry[4 * i + 3]), a.inv_oscale, rr[i].w));
+        for (int half = 0; half < 2; ++half) {
+          uint32_t ry[32];
+          tmem_ld32_async(tmem_base + lane_addr + y_col(j) + 32 * half, ry);
+          tmem_wait_ld();
+          float4 nx[8];
+          if (half == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) nx[i] = rp[8 + i];
+          }
+          if (is_q) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              op[8 * half + i] = make_float4(fmaf(__uint_as_float(ry[4 * i]), a.inv_oscale, rr[i].x), fmaf(__uint_as_float(ry[4 * i + 1]), a.inv_oscale, rr[i].y),
+                                             fmaf(__uint_as_float(ry[4 * i + 2]), a.inv_oscale, rr[i].z), fmaf(__uint_as_float(ry[4 * i + 3]), a.inv_oscale, rr[i].w));
+          }
+          if (half == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rr[i] = nx[i];
           }
         }
         tc_fence_before();
@@ -464,7 +525,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
     }
     if (tr) for (int i = 0; i < 12; ++i) a.trace[16 * j + i] = (unsigned long long)tc_[i];
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;" ::: "memory");
   }
   if (warp == MMA_WARP || warp == MMA_WARP + 1) {
     // ======================================================================= MMA issuers: warp 8 lane 0 -> tile 0 (+ weight images), warp 9 lane 0 -> tile 1
@@ -499,11 +560,14 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
         ttc_tiles(sg, band, tl);
         const TtcTile T = j ? tl[1] : tl[0];
         const bool act = T.r1 > T.r0, hq = T.q1 > T.q0;
+        // k-steps (16 keys) of P*V that can hold a band key of this tile's queries; P is zero beyond them
+        int nks = ((sg.wn < T.q1 + band ? sg.wn : T.q1 + band) - T.kb + 15) >> 4;
+        if (nks > SN / 16) nks = SN / 16;
         const uint32_t ro = (uint32_t)(T.r0 >> 3) * 1024u, ko = (uint32_t)(T.kb >> 3) * 1024u;
-        const uint64_t x_hi = make_desc(sb + XH_OFF + ro), x_lo = make_desc(sb + XL_OFF + ro);
-        const uint64_t w_hi = make_desc(sb + WQ_OFF), w_lo = make_desc(sb + WQ_OFF + 96 * 128);
-        const uint64_t qd = make_desc(sb + Q_OFF + ro), kd = make_desc(sb + K_OFF + ko);
-        const uint64_t od = make_desc(sb + O_OFF + ro), wd = make_desc(sb + WO_OFF);
+        const uint32_t x_hi = desc_lo(sb + XH_OFF + ro), x_lo = desc_lo(sb + XL_OFF + ro);
+        const uint32_t w_hi = desc_lo(sb + WQ_OFF), w_lo = desc_lo(sb + WQ_OFF + 96 * 128);
+        const uint32_t qd = desc_lo(sb + Q_OFF + ro), kd = desc_lo(sb + K_OFF + ko);
+        const uint32_t od = desc_lo(sb + O_OFF + ro), wd = desc_lo(sb + WO_OFF);
         const uint32_t d_s = tmem_base + s_col(j), d_o = tmem_base + o_col(j), d_y = tmem_base + y_col(j);
 
         auto issue_proj = [&](uint32_t itn) {
@@ -513,10 +577,10 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
           if (act) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t o = (uint64_t)(2 * ks);
-              tc_mma_f16(d_s, x_lo + o, w_hi + o, ID96, ks ? 1u : 0u);
-              tc_mma_f16(d_s, x_hi + o, w_lo + o, ID96, 1u);
-              tc_mma_f16(d_s, x_hi + o, w_hi + o, ID96, 1u);
+              const uint32_t o = (uint32_t)(2 * ks);
+              mma_ss(d_s, x_lo + o, w_hi + o, ID96, ks ? 1u : 0u);
+              mma_ss(d_s, x_hi + o, w_lo + o, ID96, 1u);
+              mma_ss(d_s, x_hi + o, w_hi + o, ID96, 1u);
             }
             tc_commit(&bars.proj_ready[j]);
           }
@@ -529,6 +593,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
         TTC_T(0);
         fence_proxy_async();
         issue_proj(it);
+#pragma unroll 1
         for (int h = 0; h < 8; ++h, ++it) {
           load_wq(it + 1);                                 // both issuers have committed this head's projections by the time kv_ready can complete
           mbar_wait(&bars.kv_ready, it & 1);
@@ -538,10 +603,10 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
           if (hq) {
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t hi = (uint64_t)(2 * ks), lo = (uint64_t)(4 + 2 * ks);
-              tc_mma_f16(d_s, qd + lo, kd + hi, ID160, ks ? 1u : 0u);
-              tc_mma_f16(d_s, qd + hi, kd + lo, ID160, 1u);
-              tc_mma_f16(d_s, qd + hi, kd + hi, ID160, 1u);
+              const uint32_t hi = (uint32_t)(2 * ks), lo = (uint32_t)(4 + 2 * ks);
+              mma_ss(d_s, qd + lo, kd + hi, ID160, ks ? 1u : 0u);
+              mma_ss(d_s, qd + hi, kd + lo, ID160, 1u);
+              mma_ss(d_s, qd + hi, kd + hi, ID160, 1u);
             }
             tc_commit(&bars.s_ready[j]);
             TTC_T(4);
@@ -552,13 +617,14 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
             tc_fence_after();
 #pragma unroll
             for (int s = 0; s < SN / 16; ++s) {
+              if (s >= nks) break;
               // keys kb + 16 s ..: chunk (kb + 16 s) >> 6, 32-byte step inside the chunk
               const uint32_t key = (uint32_t)T.kb + 16u * s;
               const uint32_t vo = (key >> 6) * 4096u + (key & 63u) * 2u;
-              const uint64_t vh = make_desc(sb + VH_OFF + vo), vl = make_desc(sb + VL_OFF + vo);
-              tc_mma_f16_ts(d_o, d_s + 80 + 8 * s, vh, ID32, s ? 1u : 0u);
-              tc_mma_f16_ts(d_o, d_s + 8 * s, vl, ID32, 1u);
-              tc_mma_f16_ts(d_o, d_s + 8 * s, vh, ID32, 1u);
+              const uint32_t vh = desc_lo(sb + VH_OFF + vo), vl = desc_lo(sb + VL_OFF + vo);
+              mma_ts(d_o, d_s + 80 + 8 * s, vh, ID32, s ? 1u : 0u);
+              mma_ts(d_o, d_s + 8 * s, vl, ID32, 1u);
+              mma_ts(d_o, d_s + 8 * s, vh, ID32, 1u);
             }
             tc_commit(&bars.o_ready[j]);
             TTC_T(7);
@@ -574,10 +640,10 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
             tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t hi = (uint64_t)(2 * ks), lo = (uint64_t)(4 + 2 * ks);
-              tc_mma_f16(d_y, od + lo, wd + hi, ID64, (h || ks) ? 1u : 0u);
-              tc_mma_f16(d_y, od + hi, wd + lo, ID64, 1u);
-              tc_mma_f16(d_y, od + hi, wd + hi, ID64, 1u);
+              const uint32_t hi = (uint32_t)(2 * ks), lo = (uint32_t)(4 + 2 * ks);
+              mma_ss(d_y, od + lo, wd + hi, ID64, (h || ks) ? 1u : 0u);
+              mma_ss(d_y, od + hi, wd + lo, ID64, 1u);
+              mma_ss(d_y, od + hi, wd + hi, ID64, 1u);
             }
             if (h == 7) tc_commit(&bars.y_ready[j]);
             ++nqj;

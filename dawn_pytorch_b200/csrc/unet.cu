@@ -739,7 +739,13 @@ int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const st
     DAWN_NCCL_OK(g_nccl.GroupEnd());
     xe = Act{h->XE, x.C, x.C, x.H, x.W};
   }
-  if (h->use_ta_tc && w.tq && h->ttc_table && temporal_tc_supported(x.C, Fe, h->cfg.win_width, hl, hl + F)) {
+  // tcgen05 kernel: one work unit per pixel while the sequence fits one 224-frame window.  Longer sequences are cut into segments that
+  // each pay the full two-tile MMA cost: between 225 and ~288 frames (a 200-frame shard plus its halos) the mma.sync kernel, which keeps
+  // the whole sequence on chip, is faster (measured 3.3 vs 4.4 ms per level-0 layer at 240 frames); beyond its limit the segments win
+  // over the unfused path again.
+  const bool ttc_ok = h->use_ta_tc && w.tq && h->ttc_table && temporal_tc_supported(x.C, Fe, h->cfg.win_width, hl, hl + F);
+  const bool fused_ok = h->use_fused_ta && w.fq && temporal_fused_supported(x.C, Fe, h->cfg.win_width, hl, hl + F);
+  if (ttc_ok && (Fe <= kTtcWindowMax || !fused_ok)) {
     // long sequences are cut into segments whose windows overlap: an in-place layer would let one segment read rows another already
     // replaced, so the input is copied aside first (sharded runs already read from the halo-extended copy)
     if (Fe > kTtcWindowMax && xe.p == dst.p) {
@@ -760,7 +766,7 @@ int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const st
     DAWN_TRY(launch_temporal_tc(a, c.st));
     return tap(c, name, dst);
   }
-  if (h->use_fused_ta && w.fq && temporal_fused_supported(x.C, Fe, h->cfg.win_width, hl, hl + F)) {
+  if (fused_ok) {
     TemporalFusedArgs a{};
     a.x = xe.p; a.ldx = xe.ld; a.res = x.p; a.ldr = x.ld; a.out = dst.p; a.ldo = dst.ld;
     a.F = Fe; a.P = P; a.q_lo = hl; a.q_hi = hl + F;

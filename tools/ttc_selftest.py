@@ -47,7 +47,8 @@ if __name__ == "__main__":
     else:
         for c in CASES:
             try:
-                r = subprocess.run([sys.executable, __file__, *map(str, c)], timeout=120, capture_output=True, text=True)
+                r = subprocess.run([sys.executable, __file__, *map(str, c)], timeout=60, capture_output=True, text=True)
                 print(r.stdout.strip() or ("NO OUTPUT rc=%d %s" % (r.returncode, r.stderr[-400:])), flush=True)
             except subprocess.TimeoutExpired:
-                print(f"ttc {c}: TIMEOUT (hang)", flush=True)
+                print(f"ttc {c}: TIMEOUT (hang) - stopping", flush=True)
+                break
