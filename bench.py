@@ -282,6 +282,17 @@ def main():
         ms_total = float(tt.item())
     ms_per_step = ms_total / args.steps
     value = args.gpus * 1000.0 / ms_per_step
+    comm = None
+    if sharded:
+        # stream time spent in the sharding collectives (CUDA events around them on the compute stream: they are serialised with the
+        # kernels, so all of it is exposed; includes waiting for the slowest rank), max over ranks
+        cm = torch.tensor([prof["comm_allreduce"]["ms"], prof["comm_halo"]["ms"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(cm, op=dist.ReduceOp.MAX)
+        comm = {"allreduce_ms": float(cm[0]) / args.steps, "halo_ms": float(cm[1]) / args.steps,
+                "exposed_ms": float(cm[0] + cm[1]) / args.steps,
+                "allreduce_calls_per_step": prof["comm_allreduce"]["count"] // args.steps, "halo_exchanges_per_step": prof["comm_halo"]["count"] // args.steps,
+                "allreduce_impl": "one kernel over NVLink peer memory (cudaIpc mailboxes)" if os.environ.get("DAWN_P2P", "1") != "0" else "ncclAllReduce",
+                "halo_impl": "pack copy + grouped ncclSend/ncclRecv with the two neighbours"}
     log(f"device-resident: {ms_per_step:.2f} ms/step")
 
     # ---------------- end to end through the C-ABI with HOST buffers (H2D inputs + D2H eps every step)
@@ -389,7 +400,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config, "roofline": roofline, "roofline_conv3_view": roofline_conv3, "roofline_hbm_view": roofline_hbm, "step_roofline": step_roof, "cpu_baseline": cpu_baseline,
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "cfg1": cfg1_gpu, "breakdown": breakdown}
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "comm": comm, "cfg1": cfg1_gpu, "breakdown": breakdown}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -60,6 +60,9 @@ struct GemmParams {
   const float* film;       // [2N] scale | shift, or null
   double gn_count;         // elements per group
   const int* skip_flag; int skip_if;   // mma.sync kernel only: return at once when *skip_flag == skip_if (device-side path selection)
+  int drain;                   // tcgen05 kernels: K panels (tc_gemm) / taps (tc_conv3) accumulated inside TMEM before the fp32 drain; 0 = default
+                               // (4 panels = K 256 / 9 taps = K 576).  The tensor core adds with round-toward-zero: un-normalised conv stacks
+                               // (LFG decoder) drain every panel / tap to keep the bias below the fp32 tolerance.
   int exp_shift;               // experiment (tcgen05 path, BN = 64): A operand stored/addressed this many rows into the swizzle atom
   unsigned long long* trace;   // optional [16] cycle counters written by CTA 0 of the tcgen05 kernel (debug)
 };

@@ -214,6 +214,9 @@ void base_params(GemmParams& p, const float* A, int lda, int Cin, int frames, in
   p.OH = Hh; p.OW = Ww; p.out_stride = 1;
   p.P = Hh * Ww;
   p.q_post_scale = 1.f;
+  // 14 convolutions without a normalisation in between: the tensor core's round-toward-zero accumulation is a systematic bias that
+  // compounds through the stack, so the TMEM accumulators are drained into RN fp32 registers after every tap / K panel (K = 64)
+  p.drain = 1;
 }
 void set_weights(GemmParams& p, const ConvPack& w) {
   p.B = w.w; p.Bimg = w.img; p.tc_scale = 1.0f / (kTcActScale * w.img_scale); p.ldb = w.ldb; p.N = w.N; p.K = w.K; p.bias = w.b;

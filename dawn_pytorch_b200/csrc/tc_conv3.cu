@@ -166,17 +166,23 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
       const uint32_t idesc2 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       constexpr uint64_t SBO_HALO = (uint64_t)(HW * 128 / 16);   // 10 pixel rows of 128 B between 8-row groups
       uint32_t ait = 0, bit = 0, cg = 0;
+      const int dt = (p.drain == 1 || p.drain == 3) ? p.drain : 9;   // taps accumulated in TMEM before a drain
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        for (int cc = 0; cc < NCH; ++cc, ++ait, ++cg) {
+        for (int cc = 0; cc < NCH; ++cc, ++ait) {
           const int sa = ait % A_STAGES;
-          const uint32_t buf = cg & 1;
-          mbar_wait(&acc_free[buf], ((cg >> 1) & 1) ^ 1);
           mbar_wait(&a_full[sa], (ait / A_STAGES) & 1);
           fence_proxy_async();
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smemA + sa * 2 * A_HALO), a_lo = a_hi + A_HALO;
-          const uint32_t d = tmem_base + buf * ACC_COLS;
+          uint32_t buf = 0, d = 0;
+          int in_group = 0;
           for (int tap = 0; tap < 9; ++tap, ++bit) {
+            if (in_group == 0) {
+              buf = cg & 1;
+              mbar_wait(&acc_free[buf], ((cg >> 1) & 1) ^ 1);
+              tc_fence_after();
+              d = tmem_base + buf * ACC_COLS;
+            }
             const int sb = bit % B_STAGES;
             mbar_wait(&b_full[sb], (bit / B_STAGES) & 1);
             tc_fence_after();
@@ -192,18 +198,18 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
               const uint64_t o = (uint64_t)(j * 2);
               if (BN == 64) {
                 // the lo panel follows the hi panel in the stage: rows 64..127 of one N=128 operand
-                tc_mma_f16(d, ahi + o, bhi + o, idesc2, (tap == 0 && j == 0) ? 0u : 1u);
+                tc_mma_f16(d, ahi + o, bhi + o, idesc2, (in_group == 0 && j == 0) ? 0u : 1u);
                 tc_mma_f16(d, alo + o, bhi + o, idesc, 1u);
               } else {
-                tc_mma_f16(d, alo + o, bhi + o, idesc, (tap == 0 && j == 0) ? 0u : 1u);
+                tc_mma_f16(d, alo + o, bhi + o, idesc, (in_group == 0 && j == 0) ? 0u : 1u);
                 tc_mma_f16(d, ahi + o, blo + o, idesc, 1u);
                 tc_mma_f16(d, ahi + o, bhi + o, idesc, 1u);
               }
             }
             tc_commit(&b_free[sb]);
+            if (++in_group == dt) { tc_commit(&acc_full[buf]); ++cg; in_group = 0; }
           }
           tc_commit(&a_free[sa]);
-          tc_commit(&acc_full[buf]);
         }
       }
     }
@@ -224,7 +230,8 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
       float acc[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-      for (int cc = 0; cc < NCH; ++cc, ++cg) {
+      const int ndrain = NCH * ((p.drain == 1 || p.drain == 3) ? 9 / p.drain : 1);
+      for (int cc = 0; cc < ndrain; ++cc, ++cg) {
         const uint32_t buf = cg & 1;
         mbar_wait(&acc_full[buf], (cg >> 1) & 1);
         tc_fence_after();

@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
     // =============================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // D f32, A/B f16, K-major
+      const int CH = (p.drain > 0 && p.drain < CHUNK) ? p.drain : CHUNK;
       uint32_t it = 0, cg = 0;
       const bool tr = (p.trace != nullptr) && blockIdx.x == 0;
       long long t_acc = 0, t_a = 0, t_b = 0, t_issue = 0, t0 = 0, t_begin = clock64();
@@ -292,8 +293,8 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
         for (int kc = 0; kc < KC; ++kc, ++it) {
           const int s = it % STAGES;
           const uint32_t round = it / STAGES;
-          const bool chunk_first = (kc % CHUNK) == 0;
-          const bool chunk_last = ((kc % CHUNK) == CHUNK - 1) || (kc == KC - 1);
+          const bool chunk_first = (kc % CH) == 0;
+          const bool chunk_last = ((kc % CH) == CH - 1) || (kc == KC - 1);
           const uint32_t buf = cg & 1;
           if (tr) t0 = clock64();
           if (chunk_first) {
@@ -350,7 +351,8 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
       float acc[EN];
 #pragma unroll
       for (int i = 0; i < EN; ++i) acc[i] = 0.f;
-      const int nchunks = (KC + CHUNK - 1) / CHUNK;
+      const int CH = (p.drain > 0 && p.drain < CHUNK) ? p.drain : CHUNK;
+      const int nchunks = (KC + CH - 1) / CH;
       for (int c = 0; c < nchunks; ++c, ++cg) {
         const uint32_t buf = cg & 1;
         const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && etid == 0;

@@ -135,6 +135,52 @@ struct UpW { ConvW cls[4]; ConvW all; };      // all: the four parity classes as
 
 using namespace dawn;
 
+// ---------------------------------------------------------------- GroupNorm all-reduce over peer memory (NVLink)
+constexpr int kP2pMaxRanks = 8, kP2pSlots = 4;
+struct P2pMail {
+  double val[kP2pSlots][kP2pMaxRanks][16];     // [ring slot][source rank][8 groups x {sum, sum of squares}]
+  unsigned int flag[kP2pSlots][kP2pMaxRanks];  // sequence number of the data in val[slot][source]
+};
+struct P2pPeers { P2pMail* m[kP2pMaxRanks]; };
+
+// One warp.  seq = ++*ctr identifies this all-reduce on every rank (all ranks issue the same sequence of calls).  Lanes 0..15 push this
+// rank's 16 doubles into every peer's mailbox (plain stores to peer-mapped memory travel over NVLink), a system-scope fence orders them
+// before the flag store; then the warp waits for all sources' flags in its own mailbox and adds the 16-vectors in rank order, so every
+// rank computes the bit-identical sum.  A rank cannot run more than one all-reduce ahead of the slowest one (it needs everyone's flag
+// of the current call), so a ring of 4 slots is never overwritten while still being read.
+__global__ void gn_p2p_allreduce_kernel(double* __restrict__ stats, P2pPeers peers, int rank, int nranks, unsigned int* ctr) {
+  const int lane = threadIdx.x;
+  unsigned int seq = 0;
+  if (lane == 0) seq = ++(*ctr);
+  seq = __shfl_sync(0xffffffffu, seq, 0);
+  const int slot = seq % kP2pSlots;
+  if (lane < 16) {
+    const double v = stats[lane];
+    for (int r = 0; r < nranks; ++r) peers.m[r]->val[slot][rank][lane] = v;
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (lane < nranks) {
+    volatile unsigned int* f = &peers.m[lane]->flag[slot][rank];
+    *f = seq;
+  }
+  P2pMail* mine = peers.m[rank];
+  if (lane < nranks) {
+    volatile unsigned int* f = &mine->flag[slot][lane];
+    const long long t0 = clock64();
+    while (*f != seq) {
+      if (clock64() - t0 > 8000000000LL) break;     // ~4 s: a peer never arrived (it failed); do not hang the GPU, the caller's checks report it
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+  if (lane < 16) {
+    double acc = 0.0;
+    for (int r = 0; r < nranks; ++r) acc += *(volatile double*)&mine->val[slot][r][lane];
+    stats[lane] = acc;
+  }
+}
+
 struct dawn_unet {
   dawn_unet_cfg cfg{};
   int nlev = 0;
@@ -192,6 +238,12 @@ struct dawn_unet {
   int sh_nranks = 1, sh_rank = 0, sh_Fglobal = 0, sh_halo_l = 0, sh_halo_r = 0;
   ncclComm_t sh_comm = nullptr;
   float* XE = nullptr;                         // (halo_l + F + halo_r) frames of a temporal layer's input, dense
+  // GroupNorm all-reduce over NVLink peer memory (one kernel: every rank stores its 16 partial sums into every peer's mailbox, then
+  // sums the mailboxes in rank order); set up by dawn_unet_shard_ipc_export / _import, otherwise ncclAllReduce is used
+  P2pMail* p2p_own = nullptr;                  // this rank's mailbox (cudaMalloc, exported through cudaIpc)
+  P2pMail* p2p_peer[kP2pMaxRanks] = {nullptr}; // every rank's mailbox as mapped into this process ([rank] == own)
+  unsigned int* p2p_ctr = nullptr;             // device-side sequence number (graph replays keep counting)
+  bool p2p_ready = false;
 
   std::map<std::string, float*> taps;
   int64_t launches = 0;
@@ -542,6 +594,8 @@ enum ProfCat : int {
   PC_PREP,           // per-clip tables
   PC_TEMPORAL_L0,    // fused per-pixel temporal attention at level 0 (the dominant kernel: bench.py's roofline object)
   PC_CONV3_L0,       // halo-tile 3x3 conv, dim -> dim channels at level 0
+  PC_COMM_AR,        // frame sharding: GroupNorm statistic all-reduces (stream time, includes waiting for the slowest rank)
+  PC_COMM_HALO,      // frame sharding: temporal halo exchange (pack copy + neighbour send/recv)
   PC_COUNT
 };
 static_assert(PC_COUNT <= DAWN_PROF_NCAT, "increase DAWN_PROF_NCAT");
@@ -635,7 +689,14 @@ int gn_allreduce(Ctx& c, int slot) {
   dawn_unet* h = c.h;
   if (h->sh_nranks <= 1) return 0;
   double* st = h->STATS + 16 * slot;
-  h->launches++;
+  ProfScope ps(c, PC_COMM_AR, 0, 128.0 * h->sh_nranks);
+  if (h->p2p_ready) {
+    P2pPeers pp;
+    for (int r = 0; r < kP2pMaxRanks; ++r) pp.m[r] = h->p2p_peer[r];
+    gn_p2p_allreduce_kernel<<<1, 32, 0, c.st>>>(st, pp, h->sh_rank, h->sh_nranks, h->p2p_ctr);
+    DAWN_LAUNCH_OK();
+    return 0;
+  }
   DAWN_NCCL_OK(g_nccl.AllReduce(st, st, 16, kNcclFloat64, kNcclSum, h->sh_comm, c.st));
   return 0;
 }
@@ -724,7 +785,7 @@ int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const st
     // K/V of those frames are re-projected locally.  Own frames are packed densely, boundaries go by NCCL send/recv.
     const size_t rowb = (size_t)x.C * sizeof(float);
     float* mid = h->XE + (size_t)hl * P * x.C;
-    h->launches++;
+    ProfScope ps(c, PC_COMM_HALO, 0, 4.0 * (2.0 * F + 2.0 * (hl + hr)) * P * x.C);
     DAWN_CUDA_OK(cudaMemcpy2DAsync(mid, rowb, x.p, (size_t)x.ld * sizeof(float), rowb, (size_t)F * P, cudaMemcpyDeviceToDevice, c.st));
     const size_t hcount = (size_t)h->cfg.win_width * P * x.C;
     DAWN_NCCL_OK(g_nccl.GroupStart());
@@ -1133,6 +1194,8 @@ void dawn_unet_destroy(dawn_unet* h) {
   if (h->samp_exec) cudaGraphExecDestroy(h->samp_exec);
   if (h->samp_stream) cudaStreamDestroy(h->samp_stream);
   if (h->sh_comm && g_nccl.ok) g_nccl.CommDestroy(h->sh_comm);
+  for (int r = 0; r < kP2pMaxRanks; ++r)
+    if (h->p2p_peer[r] && h->p2p_peer[r] != h->p2p_own) cudaIpcCloseMemHandle(h->p2p_peer[r]);
   free_all(h->owned);
   free_all(h->ws_owned);
   delete h;
@@ -1335,6 +1398,7 @@ int dawn_unet_set_num_frames(dawn_unet* h, int F, int height, int width) {
     h->cond_descs = (CondDesc*)d; h->n_cond = (int)cd.size();
   }
   h->sh_nranks = 1; h->sh_rank = 0; h->sh_Fglobal = F; h->sh_halo_l = 0; h->sh_halo_r = 0;   // a new geometry is unsharded until init_shard
+  h->p2p_ready = false;
   DAWN_TRY(launch_rotary_table(h->rot_freqs, F, 0, h->ROT, 0));
   DAWN_CUDA_OK(cudaDeviceSynchronize());
   return 0;
@@ -1493,12 +1557,53 @@ int dawn_unet_init_shard(dawn_unet* h, const char* id128, int nranks, int rank, 
     DAWN_NCCL_OK(g_nccl.CommInitRank(&h->sh_comm, nranks, id, rank));
   }
   h->sh_nranks = nranks; h->sh_rank = rank; h->sh_Fglobal = F_global;
+  h->p2p_ready = false;
   h->sh_halo_l = (rank > 0) ? h->cfg.win_width : 0;
   h->sh_halo_r = (rank < nranks - 1) ? h->cfg.win_width : 0;
   // rotary positions of the halo-extended local sequence are GLOBAL frame indices
   const int pos0 = rank * h->F - h->sh_halo_l;
   DAWN_TRY(launch_rotary_table(h->rot_freqs, h->sh_halo_l + h->F + h->sh_halo_r, pos0, h->ROT, 0));
   DAWN_CUDA_OK(cudaDeviceSynchronize());
+  return 0;
+}
+
+// Peer-memory mailboxes for the GroupNorm all-reduce: export this rank's mailbox as a cudaIpc handle (64 bytes) ...
+int dawn_unet_shard_ipc_export(dawn_unet* h, char* out64) {
+  DAWN_CHECK(h && out64, "null argument");
+  DAWN_CHECK(h->sh_nranks > 1 && h->sh_nranks <= kP2pMaxRanks, "init_shard (2..8 ranks) must precede shard_ipc_export");
+  if (!h->p2p_own) {
+    float* p = nullptr;
+    DAWN_TRY(dev_alloc(h->owned, (sizeof(P2pMail) + 3) / 4, &p));
+    h->p2p_own = reinterpret_cast<P2pMail*>(p);
+    DAWN_TRY(dev_alloc(h->owned, 4, &p));
+    h->p2p_ctr = reinterpret_cast<unsigned int*>(p);
+  }
+  DAWN_CUDA_OK(cudaMemset(h->p2p_own, 0, sizeof(P2pMail)));
+  DAWN_CUDA_OK(cudaMemset(h->p2p_ctr, 0, 16));
+  DAWN_CUDA_OK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t hd;
+  DAWN_CUDA_OK(cudaIpcGetMemHandle(&hd, h->p2p_own));
+  static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(out64, &hd, 64);
+  h->p2p_ready = false;
+  return 0;
+}
+// ... and map every rank's mailbox (handles: nranks x 64 bytes, in rank order; the own entry is not opened).  Collective in the sense
+// that every rank must have exported (and zeroed) its mailbox before any rank runs a forward: callers put a barrier after the import.
+int dawn_unet_shard_ipc_import(dawn_unet* h, const char* handles) {
+  DAWN_CHECK(h && handles, "null argument");
+  DAWN_CHECK(h->p2p_own && h->sh_nranks > 1 && h->sh_nranks <= kP2pMaxRanks, "shard_ipc_export must precede shard_ipc_import");
+  for (int r = 0; r < h->sh_nranks; ++r) {
+    if (r == h->sh_rank) { h->p2p_peer[r] = h->p2p_own; continue; }
+    if (h->p2p_peer[r]) { cudaIpcCloseMemHandle(h->p2p_peer[r]); h->p2p_peer[r] = nullptr; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handles + 64 * r, 64);
+    void* ptr = nullptr;
+    DAWN_CUDA_OK(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->p2p_peer[r] = reinterpret_cast<P2pMail*>(ptr);
+  }
+  h->p2p_ready = true;
+  drop_sampler_graph(h);
   return 0;
 }
 

@@ -8,6 +8,7 @@ The sub-modules below only HOLD parameters (names, shapes, default initialisers)
 hand-written sm_100a CUDA kernels behind the C-ABI in include/dawn_unet.h.  There is no PyTorch fallback.
 """
 import ctypes
+import os
 import math
 
 import torch
@@ -378,6 +379,16 @@ class Unet3D(nn.Module):
         dist.broadcast_object_list(box, src=0)
         with torch.cuda.device(device):
             check(lib.dawn_unet_init_shard(self._handle, box[0], world, rank, F_local * world), "dawn_unet_init_shard")
+        # GroupNorm all-reduces over NVLink peer memory (cudaIpc mailboxes) when all ranks sit on one node; DAWN_P2P=0 keeps NCCL
+        if 2 <= world <= 8 and os.environ.get("DAWN_P2P", "1") != "0":
+            hbuf = ctypes.create_string_buffer(64)
+            with torch.cuda.device(device):
+                check(lib.dawn_unet_shard_ipc_export(self._handle, hbuf), "dawn_unet_shard_ipc_export")
+            allh = [None] * world
+            dist.all_gather_object(allh, bytes(hbuf.raw))
+            with torch.cuda.device(device):
+                check(lib.dawn_unet_shard_ipc_import(self._handle, b"".join(allh)), "dawn_unet_shard_ipc_import")
+            dist.barrier()
         self._shard = (rank, world, (F_local, h, w))
         self._gen = getattr(self, "_gen", 0) + 1
 

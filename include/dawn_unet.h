@@ -64,6 +64,12 @@ int dawn_unet_set_num_frames(dawn_unet* h, int F, int height, int width);
  * (after set_num_frames with the local F).  All inputs/outputs of forward* are then the LOCAL frames. */
 int dawn_nccl_unique_id(char* out128);
 int dawn_unet_init_shard(dawn_unet* h, const char* id128, int nranks, int rank, int F_global);
+/* Optional, after init_shard (one process per GPU on ONE node, 2..8 ranks): GroupNorm statistics are then all-reduced by a single
+ * kernel over NVLink peer memory (every rank stores its 16 partial sums into every peer's mailbox and adds the mailboxes in rank
+ * order: bit-identical on all ranks) instead of ncclAllReduce.  export: this rank's mailbox as a 64-byte cudaIpc handle; exchange the
+ * handles (any host channel), then import all of them (nranks x 64 bytes, rank order) and put a barrier before the next forward. */
+int dawn_unet_shard_ipc_export(dawn_unet* h, char* out64);
+int dawn_unet_shard_ipc_import(dawn_unet* h, const char* handles);
 
 /* Clip invariants: the 272 feature channels are identical for every frame and every
  * DDIM step (reference :1167 `fea.repeat`), and cross-attention keys/values depend only on `cond`.
@@ -96,7 +102,7 @@ int dawn_unet_tap_shape(dawn_unet* h, const char* name, int* C, int* hl, int* wl
  * ca_gate, gn_hcond, attn_core, sla_context, gn_apply, rowstats, ca_rstd, misc, prep, temporal_fused_l0 (the fused
  * temporal attention launches at level 0, not counted in attn_core), conv3x3_l0 (dim -> dim 3x3 convs at level 0, not
  * counted in conv3x3). */
-#define DAWN_PROF_NCAT 16
+#define DAWN_PROF_NCAT 20
 int dawn_unet_profile_enable(dawn_unet* h, int on);
 int dawn_unet_profile_read(dawn_unet* h, double* ms, double* flops, double* bytes, int64_t* count);
 

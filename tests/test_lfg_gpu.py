@@ -26,13 +26,6 @@ def over_tol(a, ref):
     return ((a - ref).abs() / (ATOL + RTOL * ref.abs())).max().item()
 
 
-def tap_over_tol(a, ref):
-    """Internal activations reach |x| ~ 20 (He-initialised synthetic weights, no normalisation between the 14 convs): the absolute
-    part of the tolerance scales with the tensor's magnitude; the module OUTPUTS are held to the unscaled north-star tolerance."""
-    a, ref = a.detach().float().cpu(), ref.detach().float().cpu()
-    return ((a - ref).abs() / (ATOL * max(1.0, ref.abs().max().item()) + RTOL * ref.abs())).max().item()
-
-
 def probe_idx(name, numel):
     u = W.uniform01('probe/' + name, PROBE_N)
     return np.minimum((u.astype(np.float64) * numel).astype(np.int64), numel - 1)
@@ -69,13 +62,13 @@ def test_decode_matches_reference_golden(case):
     with torch.no_grad():
         L.forward_with_flow(synth_sd(), L.LfgCfg(), src, flow, occ, taps=taps_o)
     for name in ("bottleneck", "up0", "up1"):
-        print(f"{case} tap {name}: {tap_over_tol(g.read_tap(name), taps_o[name]):.3f} x (magnitude-scaled) tol")
+        print(f"{case} tap {name}: {over_tol(g.read_tap(name), taps_o[name]):.3f} x tol")
     d_def = (out["deformed"].cpu() - torch.from_numpy(gold["deformed"])).abs().max().item()
     r = over_tol(out["prediction"], torch.from_numpy(gold["prediction"]))
     print(f"{case}: prediction {r:.3f} x tol, deformed max|d| {d_def:.2e}, {g.last_launch_count()} launches")
     assert d_def < 1e-5
     for name in ("bottleneck", "up0", "up1"):
-        assert tap_over_tol(g.read_tap(name), taps_o[name]) <= 1.0, name
+        assert over_tol(g.read_tap(name), taps_o[name]) <= 1.0, name      # unscaled north-star tolerance on the un-normalised activations
     assert r <= 1.0
     assert g.last_launch_count() > 30
 
