@@ -182,6 +182,65 @@ def cpu_baseline_run(state_dict, steps, warmup):
                 sample=f"{Fs} of {F_CLIP} frames at 64x64 latent, median of {steps} forwards ({sec:.2f} s each), scaled by {Fs}/{F_CLIP}"), sec
 
 
+def clip_pipeline(rank, world, dev, dist, clips=2, steps=20, chunk=50):
+    """BASELINE configs[4] pipeline, one clip end to end from HOST buffers: source encoder + bbox embedding, `steps` DDIM steps over
+    the CUDA UNet replayed as ONE CUDA graph, batched LFG decode of the sampled flow/occlusion maps into frames, D2H of the frames.
+    N = 1: a 200-frame 256x256 clip (configs[2]'s clip).  N > 1: 100 frames per GPU as configs[3]/[4] state (400 f on 4, 800 f on 8):
+    the sampler runs frame-sharded (halo exchange, GroupNorm and quantile reductions), every rank decodes its own frames (the decoder
+    is per-frame: no exchange).  Random-init weights of the reference architecture, synthetic inputs.  Times are CUDA-event /
+    wall-clock maxima over ranks; the first clip (graph capture, allocations) is not timed."""
+    from dawn_pytorch_b200 import FlowDiffusion
+    torch.manual_seed(0)
+    Fl, S = (F_CLIP if world == 1 else 100), 4 * H_LAT
+    Fg = Fl * world
+    m = FlowDiffusion(sampling_timesteps=steps, pose_dim=6, win_width=40).to(dev)
+    m.update_num_frames(Fl)
+    if world > 1:
+        m.unet.init_shard(Fl, H_LAT, W_LAT, dev)
+    g = torch.Generator().manual_seed(7)
+    img_h = torch.rand(1, 3, S, S, generator=g).pin_memory()
+    hub_h = torch.randn(1, Fg, 1024, generator=g)[:, rank * Fl:(rank + 1) * Fl].contiguous().pin_memory()
+    pose_h = (torch.randn(1, 6, Fg, generator=g) * 0.2)[:, :, rank * Fl:(rank + 1) * Fl].contiguous().pin_memory()
+    eye_h = torch.rand(1, 2, Fg, generator=g)[:, :, rank * Fl:(rank + 1) * Fl].contiguous().pin_memory()
+    bbox = torch.tensor([[0.3 * S, 0.7 * S, 0.25 * S, 0.8 * S, S, S]]).unsqueeze(-1).repeat(1, 1, Fl)
+    out_h = torch.empty((Fl, 3, S, S), dtype=torch.float32).pin_memory()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    stage, wall = [], []
+    for clip in range(clips + 1):
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        img, hub, pose, eye = img_h.to(dev, non_blocking=True), hub_h.to(dev, non_blocking=True), pose_h.to(dev, non_blocking=True), eye_h.to(dev, non_blocking=True)
+        ev[0].record()
+        fea = m.generator.compute_fea(img)
+        mask = m.face_loc_emb(m.generate_bbox_mask(bbox.to(dev), size=S))
+        cond = torch.cat([hub, pose.permute(0, 2, 1), eye.permute(0, 2, 1)], dim=-1)      # (1, F, 1024 + 6 + 2), synthetic deltas (FD:350)
+        ev[1].record()
+        pred = m.diffusion.ddim_sample(torch.cat([fea, mask], dim=1), (1, 3, Fl, H_LAT, W_LAT), cond=cond, use_graph=True, seed=1234 + clip)
+        ev[2].record()
+        for i in range(0, Fl, chunk):
+            out_h[i:i + chunk].copy_(m.generator.decode_sample(img, pred[0][:, i:i + chunk].contiguous()), non_blocking=True)
+        ev[3].record()
+        torch.cuda.synchronize()
+        if clip > 0:
+            wall.append(time.perf_counter() - t0)
+            stage.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
+    t = torch.tensor([statistics.median(wall)] + [statistics.median(x) for x in zip(*stage)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall_s, prep, samp, dec = [float(v) for v in t]
+    finite = bool(torch.isfinite(out_h).all())
+    del m
+    torch.cuda.empty_cache()
+    return {"workload": (f"configs[4] pipeline: one {Fg}-frame 256x256 clip, {steps} DDIM steps (one CUDA graph) + batched LFG decode, "
+                         + ("single GPU" if world == 1 else f"{Fl} frames per GPU, sampler frame-sharded x{world}, decode per rank")),
+            "clips_per_s": 1.0 / wall_s, "frames_per_s": Fg / wall_s, "ms_per_clip_e2e": wall_s * 1e3,
+            "stage_ms": {"source_encoder_and_bbox": prep, "sampling": samp, "sampling_per_step": samp / steps, "lfg_decode_and_d2h": dec},
+            "h2d_bytes_per_clip": int(img_h.numel() + hub_h.numel() + pose_h.numel() + eye_h.numel()) * 4, "d2h_bytes_per_clip": int(out_h.numel()) * 4,
+            "timed_clips": clips, "finite": finite}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -190,6 +249,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent clips per GPU instead of one frame-sharded clip")
+    ap.add_argument("--no-clip", action="store_true", help="skip the whole-clip pipeline (configs[4]) measurement")
     ap.add_argument("--cpu-baseline-worker", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -315,6 +375,14 @@ def main():
     d2h = out_h.numel() * 4
     e2e = {"value": args.gpus * args.steps / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "note": "dawn_unet_forward_host: per step H2D of x_t+fea+cond+t, clip-invariant tables rebuilt, forward, D2H of eps"}
+    clip = None
+    if not args.no_clip and not args.replicas:
+        try:
+            del out_h
+            clip = clip_pipeline(rank, world, dev, dist)
+            log(f"clip pipeline: {clip['ms_per_clip_e2e']:.1f} ms per clip")
+        except Exception as e:  # noqa: BLE001
+            clip = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -400,7 +468,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config, "roofline": roofline, "roofline_conv3_view": roofline_conv3, "roofline_hbm_view": roofline_hbm, "step_roofline": step_roof, "cpu_baseline": cpu_baseline,
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "comm": comm, "cfg1": cfg1_gpu, "breakdown": breakdown}
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "comm": comm, "clip": clip, "cfg1": cfg1_gpu, "breakdown": breakdown}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

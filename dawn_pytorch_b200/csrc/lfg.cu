@@ -215,8 +215,10 @@ void base_params(GemmParams& p, const float* A, int lda, int Cin, int frames, in
   p.P = Hh * Ww;
   p.q_post_scale = 1.f;
   // 14 convolutions without a normalisation in between: the tensor core's round-toward-zero accumulation is a systematic bias that
-  // compounds through the stack, so the TMEM accumulators are drained into RN fp32 registers after every tap / K panel (K = 64)
-  p.drain = 1;
+  // compounds through the stack, so the TMEM accumulators are drained into RN fp32 registers every 3 taps / K panels (K = 192) instead
+  // of every 9 / 4.  Measured on B200 (internal taps against the oracle, unscaled tolerance): default 0.98-1.31 x tol, every tap
+  // 0.10-0.17 x tol at +20 % decode time; every third tap keeps ~3x headroom at a third of that cost.
+  p.drain = 3;
 }
 void set_weights(GemmParams& p, const ConvPack& w) {
   p.B = w.w; p.Bimg = w.img; p.tc_scale = 1.0f / (kTcActScale * w.img_scale); p.ldb = w.ldb; p.N = w.N; p.K = w.K; p.bias = w.b;
