@@ -347,9 +347,14 @@ def main():
         # stream time spent in the sharding collectives (CUDA events around them on the compute stream: they are serialised with the
         # kernels, so all of it is exposed; includes waiting for the slowest rank), max over ranks
         cm = torch.tensor([prof["comm_allreduce"]["ms"], prof["comm_halo"]["ms"]], device=dev, dtype=torch.float64)
+        cmin = cm.clone()
         dist.all_reduce(cm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cmin, op=dist.ReduceOp.MIN)
+        # max over ranks includes the time the lightly loaded edge ranks (one halo) wait for the interior ranks (two halos: the critical
+        # path); min over ranks is what the collectives cost the slowest rank itself
         comm = {"allreduce_ms": float(cm[0]) / args.steps, "halo_ms": float(cm[1]) / args.steps,
                 "exposed_ms": float(cm[0] + cm[1]) / args.steps,
+                "allreduce_ms_min_rank": float(cmin[0]) / args.steps, "halo_ms_min_rank": float(cmin[1]) / args.steps,
                 "allreduce_calls_per_step": prof["comm_allreduce"]["count"] // args.steps, "halo_exchanges_per_step": prof["comm_halo"]["count"] // args.steps,
                 "allreduce_impl": "one kernel over NVLink peer memory (cudaIpc mailboxes)" if os.environ.get("DAWN_P2P", "1") != "0" else "ncclAllReduce",
                 "halo_impl": "pack copy + grouped ncclSend/ncclRecv with the two neighbours"}
