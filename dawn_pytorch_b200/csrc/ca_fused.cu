@@ -271,7 +271,33 @@ int launch_ci(CaFusedArgs a, cudaStream_t st) {
 // a1 = SiLU(FiLM(GroupNorm(y))) + Wt (M x 32) * T_f (32 x co)      (first half of a conditioned ResnetBlock, U:366-380, 454-463)
 // A streaming kernel: Wt rows arrive straight in A-fragment order from global memory, the frame's table T_f sits in shared memory as
 // fp16 hi|lo, the K = 32 product is 6 mma.sync per 8 channels, and the epilogue reads y / writes a1 in 32-byte quad segments.
-__global__ void __launch_bounds__(NTH) gn_hcond_kernel(GnHcondArgs a) {
+// (x0, x1) -> packed fp16 hi pair / lo pair with the round-to-nearest 11-bit split of the tcgen05 producers (tc_common.cuh split_f16x2)
+__device__ __forceinline__ void split_rn(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const float h0 = __uint_as_float((__float_as_uint(x0) + 0x1000u) & 0xFFFFE000u);
+  const float h1 = __uint_as_float((__float_as_uint(x1) + 0x1000u) & 0xFFFFE000u);
+  const __half2 h = __floats2half2_rn(h0, h1);
+  const __half2 l = __floats2half2_rn(x0 - h0, x1 - h1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// transpose the 4 x 4 matrix M[lane t of the quad][i] in place: afterwards v[j] = what lane j held in its v[t]
+__device__ __forceinline__ void quad_transpose(uint32_t (&v)[4], int t) {
+  {   // exchange 2 x 2 blocks with the lane two away
+    const bool up = (t & 2) != 0;
+    const uint32_t s0 = up ? v[0] : v[2], s1 = up ? v[1] : v[3];
+    const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 2), r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+    if (up) { v[0] = r0; v[1] = r1; } else { v[2] = r0; v[3] = r1; }
+  }
+  {   // exchange single elements with the neighbouring lane
+    const bool up = (t & 1) != 0;
+    const uint32_t s0 = up ? v[0] : v[1], s1 = up ? v[2] : v[3];
+    const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    if (up) { v[0] = r0; v[2] = r1; } else { v[1] = r0; v[3] = r1; }
+  }
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(NTH, 3) gn_hcond_kernel(GnHcondArgs a) {
   constexpr int TLD = 40;
   extern __shared__ __align__(16) unsigned char gh_smem[];
   __half* Th = reinterpret_cast<__half*>(gh_smem);      // [co][TLD]  B operand: rows = output channel, k = table row
@@ -330,6 +356,7 @@ __global__ void __launch_bounds__(NTH) gn_hcond_kernel(GnHcondArgs a) {
         yv[n][0] = __ldg(reinterpret_cast<const float2*>(y0 + n0 + n * 8 + 2 * t));
         yv[n][1] = __ldg(reinterpret_cast<const float2*>(y1 + n0 + n * 8 + 2 * t));
       }
+      uint32_t sh[2][4], sl[2][4];                      // split-output mode: packed (c, c+1) pairs per n-block, rows g / g+8
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -345,8 +372,27 @@ __global__ void __launch_bounds__(NTH) gn_hcond_kernel(GnHcondArgs a) {
         const float2 al2 = *reinterpret_cast<const float2*>(s_al + c), be2 = *reinterpret_cast<const float2*>(s_be + c);
         const float t00 = yv[n][0].x * al2.x + be2.x, t01 = yv[n][0].y * al2.y + be2.y;
         const float t10 = yv[n][1].x * al2.x + be2.x, t11 = yv[n][1].y * al2.y + be2.y;
-        *reinterpret_cast<float2*>(o0 + c) = make_float2(silu(t00) + acc[0], silu(t01) + acc[1]);
-        *reinterpret_cast<float2*>(o1 + c) = make_float2(silu(t10) + acc[2], silu(t11) + acc[3]);
+        const float r00 = silu(t00) + acc[0], r01 = silu(t01) + acc[1], r10 = silu(t10) + acc[2], r11 = silu(t11) + acc[3];
+        if (!SPLIT) {
+          *reinterpret_cast<float2*>(o0 + c) = make_float2(r00, r01);
+          *reinterpret_cast<float2*>(o1 + c) = make_float2(r10, r11);
+        } else {
+          split_rn(r00, r01, sh[0][n], sl[0][n]);
+          split_rn(r10, r11, sh[1][n], sl[1][n]);
+        }
+      }
+      if (SPLIT) {
+        // 4 x 4 transpose inside the quad (lane t holds the column pairs 2t, 2t+1 of the four 8-column blocks; afterwards it holds the
+        // whole block t): every lane then writes 16 contiguous bytes per row and plane, a full 64-byte run per quad
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          quad_transpose(sh[r], t);
+          quad_transpose(sl[r], t);
+          const size_t row = (r ? row1 : row0);
+          const size_t off = row * (size_t)co + n0 + 8 * t;
+          *reinterpret_cast<uint4*>(a.Out16h + off) = make_uint4(sh[r][0], sh[r][1], sh[r][2], sh[r][3]);
+          *reinterpret_cast<uint4*>(a.Out16l + off) = make_uint4(sl[r][0], sl[r][1], sl[r][2], sl[r][3]);
+        }
       }
     }
   }
@@ -362,13 +408,15 @@ int launch_gn_hcond(const GnHcondArgs& a_in, cudaStream_t st) {
   const size_t smem = (size_t)2 * a.co * 40 * 2 + (size_t)2 * a.co * 4;
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
-    DAWN_CUDA_OK(cudaFuncSetAttribute(gn_hcond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DAWN_CUDA_OK(cudaFuncSetAttribute(gn_hcond_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DAWN_CUDA_OK(cudaFuncSetAttribute(gn_hcond_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
   int px = 512;
   while (px > 128 && a.F * ((a.P + px - 1) / px) < 2 * 148) px >>= 1;     // enough CTAs to fill the SMs on the small levels
   a.px_per_cta = px;
-  gn_hcond_kernel<<<dim3((a.P + px - 1) / px, a.F), NTH, smem, st>>>(a);
+  if (a.Out16h != nullptr) gn_hcond_kernel<true><<<dim3((a.P + px - 1) / px, a.F), NTH, smem, st>>>(a);
+  else gn_hcond_kernel<false><<<dim3((a.P + px - 1) / px, a.F), NTH, smem, st>>>(a);
   DAWN_LAUNCH_OK();
   return 0;
 }

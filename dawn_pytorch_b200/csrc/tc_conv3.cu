@@ -9,8 +9,13 @@
 // Everything else follows tc_gemm.cu: FP16x3 split precision, TMEM double-buffered accumulators drained into RN fp32
 // registers (once per 64-channel chunk = 108 MMAs), persistent warp-specialised CTA (8 producer warps, 4/8 epilogue warps,
 // MMA issuer, weight loader), row-per-thread epilogue with bias + GroupNorm partial statistics.
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cstdlib>
+#include <cstring>
+#include <string>
+#include <map>
+#include <tuple>
 #include "common.cuh"
 #include "gemm.cuh"
 #include "tc_common.cuh"
@@ -46,9 +51,15 @@ struct CCfg {
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
 };
 
-template <int BN>
+// A-operand source: TMA = false: fp32 activations, gathered / split / swizzled by the 8 producer warps.  TMA = true: the activation exists as
+// two dense fp16 planes (hi | lo, written by the producing kernel's epilogue) and ONE thread fetches the halo tile of a 64-channel chunk with
+// two cp.async.bulk.tensor loads (4-D tiled map {C, W, H, F}, box {64, 10, 18, 1}, 128-byte swizzle, out-of-image rows zero-filled by the
+// TMA unit): the smem image is byte-identical to what the producers write (row = hy * 10 + hx of 128 B, absolute-address swizzle).
+template <int BN, bool TMA>
 __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const GemmParams p, const float* __restrict__ Bimg,
-                                                                          int tiles_y, int tiles_x, int tiles_n) {
+                                                                          int tiles_y, int tiles_x, int tiles_n,
+                                                                          const __grid_constant__ CUtensorMap tm_hi,
+                                                                          const __grid_constant__ CUtensorMap tm_lo) {
   using C = CCfg<BN>;
   constexpr int B_PANEL = C::B_PANEL, A_STAGES = C::A_STAGES, B_STAGES = C::B_STAGES, NWG = C::NWG;
   constexpr int MMA_WARP = C::MMA_WARP, LOAD_WARP = C::LOAD_WARP, TMEM_COLS = C::TMEM_COLS, ACC_COLS = C::ACC_COLS;
@@ -64,7 +75,7 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
   uint8_t* smemE = smemB + C::B_BYTES;
 
   if (tid == 0) {
-    for (int s = 0; s < A_STAGES; ++s) { mbar_init(&a_full[s], NPROD); mbar_init(&a_free[s], 1); }
+    for (int s = 0; s < A_STAGES; ++s) { mbar_init(&a_full[s], TMA ? 1 : NPROD); mbar_init(&a_free[s], 1); }
     for (int s = 0; s < B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_free[s], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     mbar_init(&acc_free[0], 128 * NWG); mbar_init(&acc_free[1], 128 * NWG);
@@ -92,7 +103,28 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
     y0 = (r / tiles_x) * TH; x0 = (r % tiles_x) * TW;
   };
 
-  if (warp < 8) {
+  if (TMA && warp < 8) {
+    // =============================================================== TMA producer: one thread, two tensor loads per (tile, chunk)
+    if (tid == 0) {
+      const uint64_t mh = reinterpret_cast<uint64_t>(&tm_hi), ml = reinterpret_cast<uint64_t>(&tm_lo);
+      uint32_t ait = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int f, y0, x0, nt;
+        decode(tile, f, y0, x0, nt);
+        for (int cc = 0; cc < NCH; ++cc, ++ait) {
+          const int s = ait % A_STAGES;
+          mbar_wait(&a_free[s], ((ait / A_STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&a_full[s], 2 * HROWS * 128);
+          const uint32_t dst = smem_u32(smemA + s * 2 * A_HALO), bar = smem_u32(&a_full[s]);
+          const int c0 = cc * 64, c1 = x0 - 1, c2 = y0 - 1;
+          asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                       ::"r"(dst), "l"(mh), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(f) : "memory");
+          asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                       ::"r"(dst + A_HALO), "l"(ml), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(f) : "memory");
+        }
+      }
+    }
+  } else if (warp < 8) {
     // =============================================================== producers: halo tile of one 64-channel chunk
     const int c16 = tid & 7;
     const int r0 = tid >> 3;                                   // halo rows r0 + 32 q, q = 0..5 (< 180)
@@ -306,13 +338,45 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
   }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int halo_tensor_map(const void* plane, int Cin, int W, int H, int F, CUtensorMap* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    DAWN_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !ptr) { set_last_error("cuTensorMapEncodeTiled is not available in this driver"); return -2; }
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  // one map per (plane, geometry): encoding costs microseconds but the activations of a handle live at fixed addresses
+  static std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> cache;
+  const auto key = std::make_tuple(plane, Cin, W, H, F);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return 0; }
+  const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)F};
+  const cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+  const cuuint32_t box[4] = {64, (cuuint32_t)HW, (cuuint32_t)HH, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap m;
+  const CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(plane), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r)); return -2; }
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return 0;
+}
+
 template <int BN>
 int launch_c3(const GemmParams& p, const float* Bimg, cudaStream_t st) {
   using C = CCfg<BN>;
   static bool attr_set = false;
   static int num_sms = 0;
   if (!attr_set) {
-    DAWN_CUDA_OK(cudaFuncSetAttribute(tc_conv3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_DYN));
+    DAWN_CUDA_OK(cudaFuncSetAttribute(tc_conv3_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_DYN));
+    DAWN_CUDA_OK(cudaFuncSetAttribute(tc_conv3_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_DYN));
     int dev = 0;
     DAWN_CUDA_OK(cudaGetDevice(&dev));
     DAWN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -321,7 +385,15 @@ int launch_c3(const GemmParams& p, const float* Bimg, cudaStream_t st) {
   const int tiles_y = p.IH / TH, tiles_x = p.IW / TW, tiles_n = p.N / BN;
   const int F = p.M / (p.IH * p.IW);
   const int grid = std::min(F * tiles_y * tiles_x * tiles_n, num_sms);
-  tc_conv3_kernel<BN><<<grid, C::NTHREADS, C::SMEM_DYN, st>>>(p, Bimg, tiles_y, tiles_x, tiles_n);
+  if (p.A16h != nullptr && p.A16l != nullptr) {
+    CUtensorMap mh, ml;
+    if (halo_tensor_map(p.A16h, p.Cin, p.IW, p.IH, F, &mh) != 0 || halo_tensor_map(p.A16l, p.Cin, p.IW, p.IH, F, &ml) != 0) return -2;
+    tc_conv3_kernel<BN, true><<<grid, C::NTHREADS, C::SMEM_DYN, st>>>(p, Bimg, tiles_y, tiles_x, tiles_n, mh, ml);
+  } else {
+    CUtensorMap dummy;
+    memset(&dummy, 0, sizeof(dummy));
+    tc_conv3_kernel<BN, false><<<grid, C::NTHREADS, C::SMEM_DYN, st>>>(p, Bimg, tiles_y, tiles_x, tiles_n, dummy, dummy);
+  }
   DAWN_LAUNCH_OK();
   return 0;
 }

@@ -194,6 +194,9 @@ struct dawn_unet {
   bool use_presplit = true;                    // fp16 hi|lo pre-split of A for multi-n-tile 3x3 convs (DAWN_PRESPLIT=0: off)
   bool use_fused_ca = true;                    // fused cross-attention gate kernel for ci <= 128 (DAWN_FUSED_CA=0: unfused)
   bool use_fused_sla = true;                   // fused SLA context on 64-channel levels (DAWN_FUSED_SLA=0: unfused)
+  int conv3_tma = 1;                           // halo conv fed by TMA from fp16 hi|lo planes: 1 (default) = second conv of a ResBlock, whose input the
+                                               // GroupNorm/cross-attention kernel writes pre-split; 2 = every halo conv through a split pass
+                                               // (measurement only); 0 = off (DAWN_CONV3_TMA)
   bool use_ta_tc = true;                       // tcgen05 temporal attention on 64-channel levels (DAWN_TA_TC=0: mma.sync kernel)
   bool use_fused_ta = true;                    // fused per-pixel temporal attention on 64-channel levels (DAWN_FUSED_TA=0: unfused)
   bool use_attn_tc = true;                     // tensor-core attention core (DAWN_ATTN_TC=0 falls back to SIMT)
@@ -631,6 +634,18 @@ int Ctx::gemm(const GemmParams& p, int epi, int cat) {
   if (p.Res) bytes += 4.0 * p.M * p.N;
   if (p.Y) bytes += 4.0 * p.M * p.N;
   if (epi == EPI_CA_GATE) bytes = 4.0 * p.M * (p.Cin + 24.0);
+  if (h->use_tc && h->use_conv3 && h->conv3_tma == 2 && p.Bimg != nullptr && tc_conv3_supported(p, epi) && p.A16h == nullptr && p.lda == p.Cin) {
+    // measurement mode (DAWN_CONV3_TMA=2): every halo conv fed by TMA; the planes come from a stand-alone split pass (timed under "misc")
+    GemmParams q = p;
+    unsigned short* hi = reinterpret_cast<unsigned short*>(h->O);
+    q.A16h = hi; q.A16l = hi + (size_t)p.M * p.Cin;
+    {
+      ProfScope ps0(*this, PC_MISC, 0, 8.0 * p.M * p.Cin);
+      DAWN_TRY(launch_split_rows(p.A, p.lda, p.Cin, p.M, (void*)q.A16h, (void*)q.A16l, st));
+    }
+    ProfScope ps(*this, cat, flops, bytes);
+    return launch_tc_conv3(q, q.Bimg, st);
+  }
   ProfScope ps(*this, cat, flops, bytes);
   if (h->use_tc && h->use_conv3 && p.Bimg != nullptr && tc_conv3_supported(p, epi)) return launch_tc_conv3(p, p.Bimg, st);
   if (h->use_tc && p.Bimg != nullptr && tc_gemm_supported(p, epi)) {
@@ -675,10 +690,12 @@ int ln_gemm(Ctx& c, GemmParams& p, int epi, int cat, const float* x, int ldx, in
 }
 
 // conv k x k, stride 1, same padding, + bias, optional GroupNorm statistics slot
-int conv_same(Ctx& c, const Act& in, const ConvW& w, int k, const Act& out, int stat_slot) {
+int conv_same(Ctx& c, const Act& in, const ConvW& w, int k, const Act& out, int stat_slot, const unsigned short* in16h = nullptr,
+              const unsigned short* in16l = nullptr) {
   GemmParams p; base_params(p, in, c.h->F);
   set_weights(p, w); set_square_taps(p, k, k / 2);
   p.Out = out.p; p.ldo = out.ld;
+  p.A16h = in16h; p.A16l = in16l;               // the input exists as fp16 hi | lo planes (and NOT as fp32): halo conv by TMA
   if (stat_slot >= 0) { p.stats = c.h->STATS + 16 * stat_slot; p.cpg = w.N / 8; }
   const bool l0 = in.H == c.h->lH[0] && in.C == c.h->cfg.dim && w.N == c.h->cfg.dim;
   return c.gemm(p, EPI_PLAIN, k == 3 ? (l0 ? PC_CONV3_L0 : PC_CONV3) : PC_CONV_OTHER);
@@ -725,9 +742,22 @@ int resblock(Ctx& c, const ResBlockW& r, const Act& x, const Act& out) {
   }
   DAWN_TRY(conv_same(c, x, r.c1, 3, y, r.st1));
   DAWN_TRY(gn_allreduce(c, r.st1));
+  // a1 is consumed by the second conv only: when that conv runs on the halo-tile tcgen05 kernel, a1 is written as two fp16 planes
+  // (hi | lo, the same bytes as the fp32 row) and the conv fetches its tiles by TMA
+  const unsigned short *a1h = nullptr, *a1l = nullptr;
+  if (r.cond && h->use_fused_ca && gn_hcond_supported(r.co, P) && h->conv3_tma >= 1 && h->use_tc && h->use_conv3 && r.c2.img != nullptr) {
+    GemmParams q; base_params(q, a1, F);
+    set_weights(q, r.c2); set_square_taps(q, 3, 1);
+    q.Out = y.p; q.ldo = y.ld; q.stats = h->STATS + 16 * r.st2; q.cpg = r.co / 8;
+    if (tc_conv3_supported(q, EPI_PLAIN)) {
+      a1h = reinterpret_cast<const unsigned short*>(h->A1);
+      a1l = a1h + (size_t)M * r.co;
+    }
+  }
   if (r.cond && h->use_fused_ca && gn_hcond_supported(r.co, P)) {
     GnHcondArgs a{};
     a.Wt = h->WT; a.T = r.T; a.ldbT = r.ldbT; a.Y = y.p; a.ldy = y.ld; a.Out = a1.p; a.ldo = a1.ld;
+    a.Out16h = const_cast<unsigned short*>(a1h); a.Out16l = const_cast<unsigned short*>(a1l);
     a.F = F; a.P = P; a.co = r.co;
     a.gn_stats = h->STATS + 16 * r.st1; a.gn_count = count; a.cpg = r.co / 8;
     a.gn_w = r.gn1w; a.gn_b = r.gn1b; a.film = r.film;
@@ -748,7 +778,7 @@ int resblock(Ctx& c, const ResBlockW& r, const Act& x, const Act& out) {
     DAWN_TRY(launch_gn_apply(y.p, y.ld, r.co, M, h->STATS + 16 * r.st1, count, r.co / 8, r.gn1w, r.gn1b, nullptr,
                              nullptr, 0, a1.p, a1.ld, c.st));
   }
-  DAWN_TRY(conv_same(c, a1, r.c2, 3, y, r.st2));
+  DAWN_TRY(conv_same(c, a1, r.c2, 3, y, r.st2, a1h, a1l));
   DAWN_TRY(gn_allreduce(c, r.st2));
   const float* res = x.p; int ldr = x.ld;
   if (r.res) {
@@ -1170,6 +1200,7 @@ int dawn_unet_create(const dawn_unet_cfg* cfg, dawn_unet** out) {
   { const char* e = getenv("DAWN_ATTN_TC"); h->use_attn_tc = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_FUSED_TA"); h->use_fused_ta = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_TA_TC"); h->use_ta_tc = !(e && e[0] == '0'); }
+  { const char* e = getenv("DAWN_CONV3_TMA"); h->conv3_tma = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }
   { const char* e = getenv("DAWN_FUSED_SLA"); h->use_fused_sla = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_FUSED_CA"); h->use_fused_ca = !(e && e[0] == '0'); }
   { const char* e = getenv("DAWN_PRESPLIT"); h->use_presplit = !(e && e[0] == '0'); }
