@@ -55,7 +55,7 @@ struct CCfg {
 // two dense fp16 planes (hi | lo, written by the producing kernel's epilogue) and ONE thread fetches the halo tile of a 64-channel chunk with
 // two cp.async.bulk.tensor loads (4-D tiled map {C, W, H, F}, box {64, 10, 18, 1}, 128-byte swizzle, out-of-image rows zero-filled by the
 // TMA unit): the smem image is byte-identical to what the producers write (row = hy * 10 + hx of 128 B, absolute-address swizzle).
-template <int BN, bool TMA>
+template <int BN, bool TMA, bool TR>
 __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const GemmParams p, const float* __restrict__ Bimg,
                                                                           int tiles_y, int tiles_x, int tiles_n,
                                                                           const __grid_constant__ CUtensorMap tm_hi,
@@ -199,10 +199,16 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
       constexpr uint64_t SBO_HALO = (uint64_t)(HW * 128 / 16);   // 10 pixel rows of 128 B between 8-row groups
       uint32_t ait = 0, bit = 0, cg = 0;
       const int dt = (p.drain == 1 || p.drain == 3) ? p.drain : 9;   // taps accumulated in TMEM before a drain
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const bool tr = TR && (p.trace != nullptr) && blockIdx.x == 0;
+      long long t_acc = 0, t_a = 0, t_b = 0, t_issue = 0, t0 = 0;
+      const long long t_begin = clock64();
+      uint32_t ntiles_done = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ntiles_done) {
         for (int cc = 0; cc < NCH; ++cc, ++ait) {
           const int sa = ait % A_STAGES;
+          if (tr) t0 = clock64();
           mbar_wait(&a_full[sa], (ait / A_STAGES) & 1);
+          if (tr) { const long long t1 = clock64(); t_a += t1 - t0; t0 = t1; }
           fence_proxy_async();
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smemA + sa * 2 * A_HALO), a_lo = a_hi + A_HALO;
@@ -211,12 +217,16 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
           for (int tap = 0; tap < 9; ++tap, ++bit) {
             if (in_group == 0) {
               buf = cg & 1;
+              if (tr) t0 = clock64();
               mbar_wait(&acc_free[buf], ((cg >> 1) & 1) ^ 1);
+              if (tr) { const long long t1 = clock64(); t_acc += t1 - t0; t0 = t1; }
               tc_fence_after();
               d = tmem_base + buf * ACC_COLS;
             }
             const int sb = bit % B_STAGES;
+            if (tr) t0 = clock64();
             mbar_wait(&b_full[sb], (bit / B_STAGES) & 1);
+            if (tr) { const long long t1 = clock64(); t_b += t1 - t0; t0 = t1; }
             tc_fence_after();
             const int ky = tap / 3, kx = tap - ky * 3;          // window start: halo pixel (ky, kx)
             const uint32_t woff = (uint32_t)((ky * HW + kx) * 128);
@@ -240,9 +250,15 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
             }
             tc_commit(&b_free[sb]);
             if (++in_group == dt) { tc_commit(&acc_full[buf]); ++cg; in_group = 0; }
+            if (tr) t_issue += clock64() - t0;
           }
           tc_commit(&a_free[sa]);
         }
+      }
+      if (tr) {
+        p.trace[0] = (unsigned long long)(clock64() - t_begin); p.trace[1] = ntiles_done;
+        p.trace[2] = (unsigned long long)t_acc; p.trace[3] = (unsigned long long)t_a;
+        p.trace[4] = (unsigned long long)t_b; p.trace[5] = (unsigned long long)t_issue;
       }
     }
   } else {
@@ -255,6 +271,33 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
     const int bar_id = 2 + wg;
     float* wbuf = reinterpret_cast<float*>(smemE) + ((wg * 4 + ew) * 32 * 20);
     uint32_t cg = 0;
+    // GroupNorm partial sums (U:230).  Reducing them per tile (16 warp reductions, shared and global atomics, two barriers) cost 7.2k of the
+    // 12.2k cycles a 64 -> 64 tile takes (cycle trace, profiles/r2_f_conv3_trace.md).  With a single n-tile every epilogue thread owns the same
+    // 64 columns for the whole persistent loop, so it keeps fp32 running sums per 8-column block and the warps reduce them (in fp64) only
+    // every 8 tiles and at the end: at most 64 values per fp32 partial sum.
+    const bool defer_stats = (p.stats != nullptr) && tiles_n == 1;
+    float gs[8], gss[8];
+    int pending = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { gs[i] = 0.f; gss[i] = 0.f; }
+    auto flush_stats = [&]() {
+      const int n0f = wg * 64;                                    // tiles_n == 1: this thread's columns never change
+#pragma unroll
+      for (int b8 = 0; b8 < 8; ++b8) {
+        double s = (double)gs[b8], ss = (double)gss[b8];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+        if (lane == 0) {
+          const int grp = (n0f + b8 * 8) / p.cpg;
+          atomicAdd(&p.stats[2 * grp], s);
+          atomicAdd(&p.stats[2 * grp + 1], ss);
+        }
+        gs[b8] = 0.f; gss[b8] = 0.f;
+      }
+      pending = 0;
+    };
+    const bool tre = TR && (p.trace != nullptr) && blockIdx.x == 0 && etid == 0 && wg == 0;
+    long long te_wait = 0, te_drain = 0, te_final = 0, te0 = 0, te_bias = 0, te_store = 0, te1 = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int f, y0, x0, nt;
       decode(tile, f, y0, x0, nt);
@@ -265,7 +308,9 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
       const int ndrain = NCH * ((p.drain == 1 || p.drain == 3) ? 9 / p.drain : 1);
       for (int cc = 0; cc < ndrain; ++cc, ++cg) {
         const uint32_t buf = cg & 1;
+        if (tre) te0 = clock64();
         mbar_wait(&acc_full[buf], (cg >> 1) & 1);
+        if (tre) { const long long t1 = clock64(); te_wait += t1 - te0; te0 = t1; }
         tc_fence_after();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -281,7 +326,9 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
         }
         tc_fence_before();
         mbar_arrive(&acc_free[buf]);
+        if (tre) te_drain += clock64() - te0;
       }
+      if (tre) te0 = clock64();
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc[i] *= p.tc_scale;
       const int oy = y0 + (row_in_tile >> 3), ox = x0 + (row_in_tile & 7);
@@ -302,8 +349,21 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
           acc[4 * i] += b.x; acc[4 * i + 1] += b.y; acc[4 * i + 2] += b.z; acc[4 * i + 3] += b.w;
         }
       }
+      if (tre) { te1 = clock64(); te_bias += te1 - te0; }
       store_rows_coalesced(wbuf, acc, p.Out, opix, p.ldo, ocol, rv, lane);
-      if (p.stats != nullptr) {
+      if (tre) te_store += clock64() - te1;
+      if (defer_stats) {
+        if (rv) {
+#pragma unroll
+          for (int b8 = 0; b8 < 8; ++b8) {
+            float s = 0.f, ss = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float x = acc[b8 * 8 + i]; s += x; ss += x * x; }
+            gs[b8] += s; gss[b8] += ss;
+          }
+        }
+        if (++pending == 8) flush_stats();
+      } else if (p.stats != nullptr) {
         if (etid < 16) s_st[etid] = 0.f;
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 #pragma unroll
@@ -327,6 +387,12 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
           if (grp >= glo && grp <= ghi) atomicAdd(&p.stats[etid], (double)s_st[etid]);
         }
       }
+      if (tre) te_final += clock64() - te0;
+    }
+    if (defer_stats && pending > 0) flush_stats();
+    if (tre) {
+      p.trace[9] = (unsigned long long)te_wait; p.trace[12] = (unsigned long long)te_drain; p.trace[10] = (unsigned long long)te_final;
+      p.trace[13] = (unsigned long long)te_bias; p.trace[14] = (unsigned long long)te_store;
     }
   }
 
@@ -375,8 +441,9 @@ int launch_c3(const GemmParams& p, const float* Bimg, cudaStream_t st) {
   static bool attr_set = false;
   static int num_sms = 0;
   if (!attr_set) {
-    DAWN_CUDA_OK(cudaFuncSetAttribute(tc_conv3_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_DYN));
-    DAWN_CUDA_OK(cudaFuncSetAttribute(tc_conv3_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_DYN));
+    DAWN_CUDA_OK(cudaFuncSetAttribute(tc_conv3_kernel<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_DYN));
+    DAWN_CUDA_OK(cudaFuncSetAttribute(tc_conv3_kernel<BN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_DYN));
+    DAWN_CUDA_OK(cudaFuncSetAttribute(tc_conv3_kernel<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_DYN));
     int dev = 0;
     DAWN_CUDA_OK(cudaGetDevice(&dev));
     DAWN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -388,11 +455,12 @@ int launch_c3(const GemmParams& p, const float* Bimg, cudaStream_t st) {
   if (p.A16h != nullptr && p.A16l != nullptr) {
     CUtensorMap mh, ml;
     if (halo_tensor_map(p.A16h, p.Cin, p.IW, p.IH, F, &mh) != 0 || halo_tensor_map(p.A16l, p.Cin, p.IW, p.IH, F, &ml) != 0) return -2;
-    tc_conv3_kernel<BN, true><<<grid, C::NTHREADS, C::SMEM_DYN, st>>>(p, Bimg, tiles_y, tiles_x, tiles_n, mh, ml);
+    tc_conv3_kernel<BN, true, false><<<grid, C::NTHREADS, C::SMEM_DYN, st>>>(p, Bimg, tiles_y, tiles_x, tiles_n, mh, ml);
   } else {
     CUtensorMap dummy;
     memset(&dummy, 0, sizeof(dummy));
-    tc_conv3_kernel<BN, false><<<grid, C::NTHREADS, C::SMEM_DYN, st>>>(p, Bimg, tiles_y, tiles_x, tiles_n, dummy, dummy);
+    if (p.trace) tc_conv3_kernel<BN, false, true><<<grid, C::NTHREADS, C::SMEM_DYN, st>>>(p, Bimg, tiles_y, tiles_x, tiles_n, dummy, dummy);
+    else tc_conv3_kernel<BN, false, false><<<grid, C::NTHREADS, C::SMEM_DYN, st>>>(p, Bimg, tiles_y, tiles_x, tiles_n, dummy, dummy);
   }
   DAWN_LAUNCH_OK();
   return 0;
