@@ -422,8 +422,10 @@ def main():
                      "alg_gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["bytes"] > 0 else None}
                  for k, v in prof.items() if v["count"] > 0}
     traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r1_k_traffic.json")
-    if os.path.exists(tpath):                        # dram bytes per launch from the committed ncu --set full capture of these launches
+    import glob
+    tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    tpath = tfiles[-1] if tfiles else ""             # newest committed ncu --set full capture (same kernels as this HEAD: profiles/README.md)
+    if tpath and os.path.exists(tpath):              # dram bytes per launch of exactly these launches
         with open(tpath) as f:
             traffic = json.load(f)
 

@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
     float* wbuf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + ((wg * 4 + ew) * 32 * 20);
     uint32_t cg = 0;
     int Te = -1;
-    long long te_wait = 0, te_final = 0, te_drain = 0;
+    long long te_wait = 0, te_final = 0, te_drain = 0, te_store = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       ++Te;
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN + wg * EN;
@@ -506,13 +506,16 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
             if (rv) p.gates[(size_t)m * 24 + ca * 8 + hd] = er / (er + en);
           }
         } else {
-          store_rows_coalesced(wbuf, acc, p.Out, opix, p.ldo, n0, rv, lane);
+          const long long ts0 = tr_e ? clock64() : 0;
+          if (!(p.exp_shift & 64)) store_rows_coalesced(wbuf, acc, p.Out, opix, p.ldo, n0, rv, lane);     // bit 6 of the debug field: skip the stores (timing experiment)
+          if (tr_e) te_store += clock64() - ts0;
         }
       }
       if (tr_e) te_final += clock64() - te0;
     }
     if (p.trace != nullptr && blockIdx.x == 0 && etid == 0 && wg == 0) {
       p.trace[9] = (unsigned long long)te_wait; p.trace[10] = (unsigned long long)te_final; p.trace[12] = (unsigned long long)te_drain;
+      p.trace[14] = (unsigned long long)te_store;
     }
   }
 

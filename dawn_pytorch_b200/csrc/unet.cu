@@ -1827,9 +1827,9 @@ int dawn_selftest_tc_gemm(int F, int H, int W, int Cin, int N, int ksize, int wi
       const double n = (double)std::max<unsigned long long>(tr[1], 1);
       printf("  trace (CTA 0, cycles/stage over %llu stages): total %.0f | MMA thread: wait acc_free %.0f, wait A %.0f, wait B %.0f, issue+commit %.0f | "
              "producer t0: load issue %.0f, wait slot %.0f, split+store %.0f | loader wait slot %.0f | epilogue t0: wait acc_full %.0f, drain %.0f, final epilogue %.0f "
-             "(scale+bias %.0f, store %.0f)\n",
+             "(scale+bias %.0f, store %.0f)%s\n",
              tr[1], tr[0] / n, tr[2] / n, tr[3] / n, tr[4] / n, tr[5] / n, tr[11] / n, tr[6] / n, tr[7] / n, tr[8] / n, tr[9] / n, tr[12] / n, tr[10] / n,
-             tr[13] / n, tr[14] / n);
+             tr[13] / n, tr[14] / n, (p.exp_shift & 64) ? "  [stores SKIPPED]" : "");
     }
   }
   if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) { set_last_error(std::string("selftest: ") + cudaGetErrorString(cudaGetLastError())); rc = -2; }
