@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
     float* wbuf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + ((wg * 4 + ew) * 32 * 20);
     uint32_t cg = 0;
     int Te = -1;
-    long long te_wait = 0, te_final = 0, te_drain = 0, te_store = 0;
+    long long te_wait = 0, te_final = 0, te_drain = 0, te_store = 0, te_pre = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       ++Te;
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN + wg * EN;
@@ -412,7 +412,12 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
             acc[4 * i] += r.x; acc[4 * i + 1] += r.y; acc[4 * i + 2] += r.z; acc[4 * i + 3] += r.w;
           }
         }
-        store_rows_coalesced(wbuf, acc, p.Out, opix, p.ldo, n0, rv, lane);
+        {
+          const long long ts0 = tr_e ? clock64() : 0;
+          if (tr_e) te_pre += ts0 - te0;
+          if (!(p.exp_shift & 64)) store_rows_coalesced(wbuf, acc, p.Out, opix, p.ldo, n0, rv, lane);     // bit 6 of the debug field: skip the stores (timing experiment)
+          if (tr_e) te_store += clock64() - ts0;
+        }
         if (p.stats != nullptr) {
           // GroupNorm partial statistics (U:230): per 8-column sub-block, reduced over the warp's 32 rows
           if (etid < 16) s_st[etid] = 0.f;
@@ -515,7 +520,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
     }
     if (p.trace != nullptr && blockIdx.x == 0 && etid == 0 && wg == 0) {
       p.trace[9] = (unsigned long long)te_wait; p.trace[10] = (unsigned long long)te_final; p.trace[12] = (unsigned long long)te_drain;
-      p.trace[14] = (unsigned long long)te_store;
+      p.trace[14] = (unsigned long long)te_store; p.trace[13] = (unsigned long long)te_pre;
     }
   }
 
