@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
   __shared__ RowInfo s_rows[3][BM];
   __shared__ float2 s_ln[8][BM];              // (mu, rstd) per tile row, ring over this CTA's tiles (producers run ahead of the epilogue)
   __shared__ float s_stat[NWG][16];
+  __shared__ __align__(16) float s_biasv[1024];  // the whole bias vector, fetched once per CTA (the per-tile __ldg round trip was 1-3k cycles of an epilogue-bound tile)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -344,6 +345,11 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
     float* wbuf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + ((wg * 4 + ew) * 32 * 20);
     uint32_t cg = 0;
     int Te = -1;
+    const bool bias_s = (p.bias != nullptr) && p.N <= 1024;
+    if (bias_s) {
+      for (int i = (tid - NPROD); i < p.N; i += 128 * NWG) s_biasv[i] = __ldg(p.bias + i);
+      asm volatile("bar.sync 4, %0;" ::"n"(128 * NWG) : "memory");
+    }
     long long te_wait = 0, te_final = 0, te_drain = 0, te_store = 0, te_pre = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       ++Te;
@@ -392,7 +398,15 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
 
       if (EPI == EPI_PLAIN) {
         const float sc = p.tc_scale;                          // undoes the exact power-of-two weight pre-scale
-        if (p.bias) {
+        if (bias_s) {
+          const float4* bp = reinterpret_cast<const float4*>(s_biasv + n0);
+#pragma unroll
+          for (int i = 0; i < EN / 4; ++i) {
+            const float4 b = bp[i];
+            acc[4 * i] = fmaf(acc[4 * i], sc, b.x); acc[4 * i + 1] = fmaf(acc[4 * i + 1], sc, b.y);
+            acc[4 * i + 2] = fmaf(acc[4 * i + 2], sc, b.z); acc[4 * i + 3] = fmaf(acc[4 * i + 3], sc, b.w);
+          }
+        } else if (p.bias) {
           const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
           for (int i = 0; i < EN / 4; ++i) {
