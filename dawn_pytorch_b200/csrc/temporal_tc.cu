@@ -1,5 +1,5 @@
 // Temporal attention of the 64-channel levels on tcgen05 (reference U:648-725 == LA:71-99, 275-342 inside Residual(PreNorm(...)),
-// U:763-765).  One work unit = one pixel's frame window (<= 224 frames) and a query range inside it; a persistent CTA per SM walks
+// U:763-765).  One work unit = one pixel's frame window (<= 240 frames) and a query range inside it; a persistent CTA per SM walks
 // the units.  Everything between the layer input and the layer output stays on chip:
 //
 //   x[w0 .. w0+wn, p, :] -> LayerNorm statistics, fp16 hi|lo split -> X (shared, K-major, 128-B swizzle)
@@ -41,7 +41,7 @@ constexpr int MMA_WARP = 8;             // warps 8, 9: MMA issuers of tile 0 / t
 constexpr float LOG2E = 1.4426950408889634f;
 
 // shared-memory map (bytes from a 1024-aligned base); every UMMA operand starts on a 1024-byte swizzle atom
-constexpr int XH_OFF = 0;                          // X hi: 224 rows x 128 B
+constexpr int XH_OFF = 0;                          // X hi: 240 rows x 128 B
 constexpr int XL_OFF = XH_OFF + WMAX * 128;
 constexpr int WQ_OFF = XL_OFF + WMAX * 128;        // W'_h hi (96 x 128 B) | lo
 constexpr int WO_OFF = WQ_OFF + 2 * 96 * 128;      // Wout_h (64 x 128 B)
@@ -242,9 +242,9 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
         float2* st = reinterpret_cast<float2*>(smem + ST_OFF);
         const float* xb = a.x + ((size_t)sg.w0 * a.P + pix) * a.ldx + 4 * l16;
         const size_t fstride = (size_t)a.P * a.ldx;
-        float4 xsec[7];                                    // rows 112 + : loaded now, consumed after the prefetched half
+        float4 xsec[8];                                    // rows 112 + : loaded now, consumed after the prefetched half
 #pragma unroll
-        for (int i = 0; i < 7; ++i) {
+        for (int i = 0; i < 8; ++i) {
           const int r = (7 + i) * 16 + rg;
           xsec[i] = (r < sg.wn) ? __ldg(reinterpret_cast<const float4*>(xb + (size_t)r * fstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
           }
         }
 #pragma unroll
-        for (int i = 0; i < 14; ++i) {
+        for (int i = 0; i < 15; ++i) {
           const int r = i * 16 + rg;
           const float4 v = i < 7 ? xpre[i < 7 ? i : 0] : xsec[i < 7 ? 0 : i - 7];
           float s = (v.x + v.y) + (v.z + v.w);

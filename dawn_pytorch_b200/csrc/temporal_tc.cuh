@@ -7,13 +7,13 @@
 
 namespace dawn {
 
-constexpr int kTtcWindowMax = 224;     // frames of one pixel held on chip per work unit
+constexpr int kTtcWindowMax = 240;     // frames of one pixel held on chip per work unit (a 200-frame shard plus one 40-frame halo fits)
 constexpr int kTtcBandMax = 40;        // |j - i| <= band, band <= 40 (reference win_width, config/DAWN_*.yaml)
 constexpr int kTtcMaxSeg = 16;
 constexpr int kTtcTable = 512;         // bias/mask table entries per head (index = key - query + kTtcTableZero)
-constexpr int kTtcTableZero = 224;
+constexpr int kTtcTableZero = 240;
 
-// One work unit = one pixel x one segment.  A segment holds window frames [w0, w0 + wn) of the on-chip sequence (wn <= 224) and produces
+// One work unit = one pixel x one segment.  A segment holds window frames [w0, w0 + wn) of the on-chip sequence (wn <= 240) and produces
 // the outputs of query frames [qa, qb); every band key of those queries lies inside the window.
 struct TtcSegment { int w0, wn, qa, qb; };
 

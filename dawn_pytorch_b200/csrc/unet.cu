@@ -830,10 +830,9 @@ int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const st
     DAWN_NCCL_OK(g_nccl.GroupEnd());
     xe = Act{h->XE, x.C, x.C, x.H, x.W};
   }
-  // tcgen05 kernel: one work unit per pixel while the sequence fits one 224-frame window.  Longer sequences are cut into segments that
-  // each pay the full two-tile MMA cost: between 225 and ~288 frames (a 200-frame shard plus its halos) the mma.sync kernel, which keeps
-  // the whole sequence on chip, is faster (measured 3.3 vs 4.4 ms per level-0 layer at 240 frames); beyond its limit the segments win
-  // over the unfused path again.
+  // tcgen05 kernel: one work unit per pixel while the sequence fits one 240-frame window (a 200-frame shard plus one halo).  Longer sequences
+  // are cut into segments that each pay the full two-tile cost: up to ~270 frames the mma.sync kernel, which keeps the whole sequence on
+  // chip, is faster; beyond its limit (a 200-frame shard with both halos = 280 frames) the segments win over the unfused path again.
   const bool ttc_ok = h->use_ta_tc && w.tq && h->ttc_table && temporal_tc_supported(x.C, Fe, h->cfg.win_width, hl, hl + F);
   const bool fused_ok = h->use_fused_ta && w.fq && temporal_fused_supported(x.C, Fe, h->cfg.win_width, hl, hl + F);
   if (ttc_ok && (Fe <= kTtcWindowMax || !fused_ok)) {

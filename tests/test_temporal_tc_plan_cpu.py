@@ -9,7 +9,7 @@ import pytest
 
 from dawn_pytorch_b200 import _lib
 
-WMAX, SN, CW, TB, TZ = 224, 160, 128, 512, 224
+WMAX, SN, CW, TB, TZ = 240, 160, 128, 512, 240
 
 
 def plan(F, band, qlo, qhi):

@@ -14,6 +14,10 @@ CASES = [  # F, P, band, q_lo, q_hi
     (64, 9, 8, 0, 64),
     (180, 6, 40, 40, 140),       # shard with halos on both sides (100 owned frames)
     (224, 6, 40, 0, 224),
+    (240, 6, 40, 0, 240),        # the largest single window
+    (240, 5, 40, 40, 240),       # edge shard: 200 owned frames + left halo
+    (240, 5, 40, 0, 200),        # edge shard: right halo
+    (241, 5, 40, 0, 241),        # one frame more: two segments
     (280, 300, 40, 40, 240),     # two segments, more units than SMs
     (400, 7, 40, 0, 400),        # long single-GPU clip: three segments
     (200, 4096, 40, 0, 200),     # the bench shape of one level-0 layer
