@@ -80,7 +80,7 @@ extern "C" int dawn_selftest_temporal_tc(int F, int P, int band, int q_lo, int q
 
   TemporalTcArgs a{};
   a.x = dx; a.ldx = 64; a.res = dres; a.ldr = 64; a.out = o1; a.ldo = 64; a.F = F; a.P = P; a.q_lo = q_lo; a.q_hi = q_hi;
-  a.Wqkv = dWq; a.Wout = dWo; a.wsum = dws; a.rot = drot; a.table = dtab; a.band = band; a.inv_wscale = iw; a.inv_oscale = io; a.dbg = ddbg;
+  a.Wqkv = dWq; a.Wout = dWo; a.rot = drot; a.table = dtab; a.band = band; a.inv_wscale = iw; a.inv_oscale = io; a.dbg = ddbg;
   int rc = launch_temporal_tc(a, 0);
   if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) { set_last_error(std::string("selftest tc: ") + cudaGetErrorString(cudaGetLastError())); rc = -2; }
   if (rc == 0 && trace48 && ms) {
@@ -130,8 +130,8 @@ extern "C" int dawn_selftest_temporal_tc(int F, int P, int band, int q_lo, int q
     const float* xr = &x[((size_t)f * P + pix) * 64];
     for (int n = 0; n < 768; ++n) {
       double acc = 0; for (int c = 0; c < 64; ++c) acc += (double)xr[c] * wqkv[(size_t)n * 64 + c];
-      raw[(size_t)f * 768 + n] = acc;
       const double val = rs[f] * (acc - mu[f] * wsum[n]);
+      raw[(size_t)f * 768 + n] = val;                      // what the projection accumulates: the kernel normalises the row first
       (n < 256 ? q[(size_t)f * 256 + n] : n < 512 ? k[(size_t)f * 256 + n - 256] : v[(size_t)f * 256 + n - 512]) = val;
     }
     for (int n = 0; n < 256; n += 2) {

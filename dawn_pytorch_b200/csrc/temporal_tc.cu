@@ -2,9 +2,9 @@
 // U:763-765).  One work unit = one pixel's frame window (<= 240 frames) and a query range inside it; a persistent CTA per SM walks
 // the units.  Everything between the layer input and the layer output stays on chip:
 //
-//   x[w0 .. w0+wn, p, :] -> LayerNorm statistics, fp16 hi|lo split -> X (shared, K-major, 128-B swizzle)
+//   x[w0 .. w0+wn, p, :] -> LayerNorm (the affine weight is folded into W'), fp16 hi|lo split -> X (shared, K-major, 128-B swizzle)
 //   per head h (8):   PROJ   [q|k|v]_h = X . W'_h^T            UMMA 128 x 96 x 64 per row tile          (SS, TMEM fp32)
-//                     E1     LN fold, rotary(q, k), split -> Q_h, K_h (rows) and V_h^T (dims x keys) in shared memory
+//                     E1     rotary(q, k), split -> Q_h, K_h (rows) and V_h^T (dims x keys) in shared memory
 //                     S      S = Q_h . K_h^T                    UMMA 128 x 160 x 32 per row tile         (SS)
 //                     E2     + relative bias / band mask (table), row softmax with warp-private rows, P = exp2(S - max) written
 //                            back IN PLACE into the S columns as packed fp16 hi | lo
@@ -51,9 +51,7 @@ constexpr int O_OFF = Q_OFF + WMAX * 128;
 constexpr int VH_OFF = O_OFF + WMAX * 128;         // V_h^T hi: 4 chunks of 64 keys, each 32 dims x 128 B
 constexpr int VL_OFF = VH_OFF + 4 * 4096;
 constexpr int TBL_OFF = VL_OFF + 4 * 4096;         // per-warpgroup bias/mask table of the current head
-constexpr int ST_OFF = TBL_OFF + 2 * kTtcTable * 4;
-constexpr int WS_OFF = ST_OFF + WMAX * 8;          // wsum[768]
-constexpr int SMEM_END = WS_OFF + 768 * 4;
+constexpr int SMEM_END = TBL_OFF + 2 * kTtcTable * 4;
 constexpr int SMEM_DYN = SMEM_END + 1024;
 constexpr int WQ_BYTES = 2 * 96 * 128, WO_BYTES = 64 * 128;
 
@@ -116,15 +114,12 @@ __device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[64], int o) {
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "r"(r[o + 0]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), "r"(r[o + 6]), "r"(r[o + 7]),
-      "r"(r[o + 8]), "r"(r[o + 9]), "r"(r[o + 10]), "r"(r[o + 11]), "r"(r[o + 12]), "r"(r[o + 13]), "r"(r[o + 14]), "r"(r[o + 15]),
-      "r"(r[o + 16]), "r"(r[o + 17]), "r"(r[o + 18]), "r"(r[o + 19]), "r"(r[o + 20]), "r"(r[o + 21]), "r"(r[o + 22]), "r"(r[o + 23]),
-      "r"(r[o + 24]), "r"(r[o + 25]), "r"(r[o + 26]), "r"(r[o + 27]), "r"(r[o + 28]), "r"(r[o + 29]), "r"(r[o + 30]), "r"(r[o + 31])
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
@@ -137,17 +132,21 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-// one element -> fp16 hi / lo bit patterns (same rounding as split_f16x2)
-__device__ __forceinline__ void split_f16(float x, uint16_t& hi, uint16_t& lo) {
-  const float h = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-  hi = __half_as_ushort(__float2half_rn(h));
-  lo = __half_as_ushort(__float2half_rn(x - h));
+// (x0, x1) -> packed fp16 hi pair and lo pair, hi = rn16(x), lo = rn16(x - hi): two packed conversions, two widenings, two subtractions
+// (tc_common's split_f16x2 rounds in integer arithmetic first: two more instructions per pair; every value split in this kernel is far
+// inside the fp16 range, so the direct conversion cannot overflow)
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 // 8 consecutive values of a row -> one 16-byte chunk of the hi half and one of the lo half of a [hi 32 | lo 32] operand row
 __device__ __forceinline__ void store_row_chunk(uint8_t* base, int row, int c8, const float (&v)[8]) {
   uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) split_f16x2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+  for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
   *reinterpret_cast<uint4*>(base + swz(row, c8)) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(base + swz(row, 4 + c8)) = make_uint4(l[0], l[1], l[2], l[3]);
 }
@@ -185,8 +184,6 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
     for (int i = tid; i < (2 * WMAX * 128) / 16; i += NTH) p0[i] = make_uint4(0, 0, 0, 0);
     uint4* p1 = reinterpret_cast<uint4*>(smem + K_OFF);
     for (int i = tid; i < (TBL_OFF - K_OFF) / 16; i += NTH) p1[i] = make_uint4(0, 0, 0, 0);
-    float* ws = reinterpret_cast<float*>(smem + WS_OFF);
-    for (int i = tid; i < 768; i += NTH) ws[i] = a.wsum[i];
   }
   fence_proxy_async();
   tc_fence_before();
@@ -208,9 +205,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
     const int wgtid = tid & 127;
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
     float* tb = reinterpret_cast<float*>(smem + TBL_OFF) + j * kTtcTable;
-    const float2* s_stat = reinterpret_cast<const float2*>(smem + ST_OFF);
-    const float* ws = reinterpret_cast<const float*>(smem + WS_OFF);
-    uint32_t ui = 0;                                       // units done by this CTA
+    const float fa = a.inv_wscale, faq = a.inv_wscale * LOG2E;      // scores live in the log2 domain
     // completed phases of the per-tile barriers (rows exist / queries exist), for this warpgroup's tile and for the other one
     uint32_t nact_own = 0, nact_oth = 0, nq_own = 0, nq_oth = 0;
     uint64_t* const proj_own = &bars.proj_ready[j];
@@ -222,7 +217,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
 
     float4 xpre[7];                                        // this thread's share of the next window's first 112 x rows, requested one unit ahead
     bool have_pre = false;
-    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ui) {
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
       const int pix = u / a.nseg;
       const TtcSegment sg = a.seg[u - pix * a.nseg];
       TtcTile tl[2];
@@ -234,12 +229,11 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
       const bool dbg = (a.dbg != nullptr) && u == 0;
 
       if (tr) t0 = clock64();
-      // ------------------------------------------------------------------ prologue: x rows -> LN statistics + fp16 split
+      // ------------------------------------------------------------------ prologue: x rows -> LayerNorm -> fp16 split
       // 16 lanes x float4 = one 64-channel row, 16 rows per pass.  The rows were requested during the previous unit's last head
       // (xpre holds them); only the first unit of a CTA loads here.
       {
         const int l16 = tid & 15, rg = tid >> 4;
-        float2* st = reinterpret_cast<float2*>(smem + ST_OFF);
         const float* xb = a.x + ((size_t)sg.w0 * a.P + pix) * a.ldx + 4 * l16;
         const size_t fstride = (size_t)a.P * a.ldx;
         float4 xsec[8];                                    // rows 112 + : loaded now, consumed after the prefetched half
@@ -268,9 +262,10 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
 #pragma unroll
           for (int o = 1; o < 16; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
           if (r < sg.wn) {
-            if (l16 == 0) st[r] = make_float2(mu, 1.0f / sqrtf(ss * (1.0f / 64.f) + 1e-5f));
+            // the normalised row goes into the projection (its affine weight is folded into W'): the accumulator needs no correction
+            const float rstd = 1.0f / sqrtf(ss * (1.0f / 64.f) + 1e-5f);
             uint32_t h0, l0, h1, l1;
-            split_f16x2(v.x, v.y, h0, l0); split_f16x2(v.z, v.w, h1, l1);
+            split2(d0 * rstd, d1 * rstd, h0, l0); split2(d2 * rstd, d3 * rstd, h1, l1);
             const uint32_t off = swz(r, l16 >> 1) + (l16 & 1) * 8;
             *reinterpret_cast<uint2*>(smem + XH_OFF + off) = make_uint2(h0, h1);
             *reinterpret_cast<uint2*>(smem + XL_OFF + off) = make_uint2(l0, l1);
@@ -279,11 +274,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
         fence_proxy_async();
         mbar_arrive(&bars.x_ready);
       }
-      // the statistics of this thread's row are written by other threads: wait until every compute thread has arrived
-      mbar_wait(&bars.x_ready, ui & 1);
       TTC_T(0);
-      const float2 stat = row_ok ? s_stat[row] : make_float2(0.f, 1.f);
-      const float fa = stat.y * a.inv_wscale, fb = -stat.y * stat.x;
       const float4* rotp = reinterpret_cast<const float4*>(a.rot + (size_t)(sg.w0 + (row_ok ? row : T.r0)) * 32);
       float inv_l = 1.f;
 
@@ -314,8 +305,6 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
             for (int i = 0; i < 32; ++i) { d[i] = __uint_as_float(rq[i]); d[32 + i] = __uint_as_float(rk[i]); d[64 + i] = __uint_as_float(rv[i]); }
           }
           if (row_ok) {
-            const float faq = fa * LOG2E, fbq = fb * LOG2E;         // scores live in the log2 domain
-            const float* wsq = ws + h * 32;
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
               float q8[8], k8[8];
@@ -324,10 +313,8 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
 #pragma unroll
               for (int pp = 0; pp < 4; ++pp) {
                 const int i = c8 * 8 + 2 * pp;
-                const float q0 = fmaf(fbq, wsq[i], faq * __uint_as_float(rq[i]));
-                const float q1 = fmaf(fbq, wsq[i + 1], faq * __uint_as_float(rq[i + 1]));
-                const float k0 = fmaf(fb, wsq[256 + i], fa * __uint_as_float(rk[i]));
-                const float k1 = fmaf(fb, wsq[256 + i + 1], fa * __uint_as_float(rk[i + 1]));
+                const float q0 = faq * __uint_as_float(rq[i]), q1 = faq * __uint_as_float(rq[i + 1]);
+                const float k0 = fa * __uint_as_float(rk[i]), k1 = fa * __uint_as_float(rk[i + 1]);
                 const float co = cs[2 * pp], si = cs[2 * pp + 1];
                 q8[2 * pp] = q0 * co - q1 * si; q8[2 * pp + 1] = q1 * co + q0 * si;
                 k8[2 * pp] = k0 * co - k1 * si; k8[2 * pp + 1] = k1 * co + k0 * si;
@@ -340,19 +327,17 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
           fence_proxy_async();
           mbar_arrive(&bars.kv_ready);
           if (row_ok) {
-            const float* wsq = ws + h * 32;
             // V_h^T: element (dim d, key = row) of chunk row >> 6
             uint8_t* vh = smem + VH_OFF + (row >> 6) * 4096 + (row & 7) * 2;
             uint8_t* vl = smem + VL_OFF + (row >> 6) * 4096 + (row & 7) * 2;
             const int cc = (row & 63) >> 3;
 #pragma unroll
-            for (int d = 0; d < 32; ++d) {
-              const float v = fmaf(fb, wsq[512 + d], fa * __uint_as_float(rv[d]));
-              uint16_t hi, lo;
-              split_f16(v, hi, lo);
-              const uint32_t off = swz(d, cc);
-              *reinterpret_cast<uint16_t*>(vh + off) = hi;
-              *reinterpret_cast<uint16_t*>(vl + off) = lo;
+            for (int d = 0; d < 32; d += 2) {
+              uint32_t hi, lo;
+              split2(fa * __uint_as_float(rv[d]), fa * __uint_as_float(rv[d + 1]), hi, lo);
+              const uint32_t o0 = swz(d, cc), o1 = swz(d + 1, cc);
+              *reinterpret_cast<uint16_t*>(vh + o0) = (uint16_t)hi; *reinterpret_cast<uint16_t*>(vh + o1) = (uint16_t)(hi >> 16);
+              *reinterpret_cast<uint16_t*>(vl + o0) = (uint16_t)lo; *reinterpret_cast<uint16_t*>(vl + o1) = (uint16_t)(lo >> 16);
             }
           }
           tc_fence_before();
@@ -410,19 +395,23 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
               m = fmaxf(m, s);
             }
           }
+          // P (fp16 pairs) over the S columns: hi at [0, 80), lo at [80, 160); zeros outside this warp's 128-key span.  Written 32 keys
+          // at a time so that the stores overlap the remaining exponentials (every S column of this row is already in registers)
+          const uint32_t c2 = (uint32_t)(cstart >> 1);
           float lsum = 0.f;
-          uint32_t ph[64], pl[64];
 #pragma unroll
-          for (int c = 0; c < CW; c += 2) {
-            const float p0 = ex2f(__uint_as_float(sv[c]) - m), p1 = ex2f(__uint_as_float(sv[c + 1]) - m);
-            lsum += p0 + p1;
-            split_f16x2(p0, p1, ph[c >> 1], pl[c >> 1]);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t ph[16], pl[16];
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              const float p0 = ex2f(__uint_as_float(sv[32 * q4 + c]) - m), p1 = ex2f(__uint_as_float(sv[32 * q4 + c + 1]) - m);
+              lsum += p0 + p1;
+              split2(p0, p1, ph[c >> 1], pl[c >> 1]);
+            }
+            tmem_st16(ts + c2 + 16 * q4, ph);
+            tmem_st16(ts + 80 + c2 + 16 * q4, pl);
           }
           inv_l = 1.0f / lsum;
-          // P (fp16 pairs) over the S columns: hi at [0, 80), lo at [80, 160); zeros outside this warp's 128-key span
-          const uint32_t c2 = (uint32_t)(cstart >> 1);
-          tmem_st32(ts + c2, ph, 0); tmem_st32(ts + c2 + 32, ph, 32);
-          tmem_st32(ts + 80 + c2, pl, 0); tmem_st32(ts + 80 + c2 + 32, pl, 32);
 #pragma unroll
           for (int b = 0; b < 10; ++b) {
             if (8 * b < (int)c2 || 8 * b >= (int)c2 + 64) { tmem_st8_zero(ts + 8 * b); tmem_st8_zero(ts + 80 + 8 * b); }
@@ -615,9 +604,10 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
             TTC_T(5);
             fence_proxy_async();
             tc_fence_after();
-#pragma unroll
-            for (int s = 0; s < SN / 16; ++s) {
-              if (s >= nks) break;
+            // a rolled loop on purpose: unrolled, the operand descriptors of all ten steps are precomputed, and the issuer (88 registers)
+            // spends longer shuffling them than the tensor pipe needs for the MMAs
+#pragma unroll 1
+            for (int s = 0; s < nks; ++s) {
               // keys kb + 16 s ..: chunk (kb + 16 s) >> 6, 32-byte step inside the chunk
               const uint32_t key = (uint32_t)T.kb + 16u * s;
               const uint32_t vo = (key >> 6) * 4096u + (key & 63u) * 2u;

@@ -1,4 +1,4 @@
-// tcgen05 temporal attention for the 64-channel levels (LayerNorm-folded QKV projection + rotary + banded attention with relative
+// tcgen05 temporal attention for the 64-channel levels (LayerNorm + QKV projection + rotary + banded attention with relative
 // position bias + out-projection + residual, all on chip); see temporal_tc.cu.
 #pragma once
 #include <cuda_runtime.h>
@@ -48,7 +48,6 @@ struct TemporalTcArgs {
   int q_lo, q_hi;                 // frames [q_lo, q_hi) produce output
   const uint8_t* Wqkv;            // [8 heads] shared-memory images: W'_h hi (96 x 128 B, swizzled) | lo; rows q 32, k 32, v 32
   const uint8_t* Wout;            // [8 heads] images: Wout_h (64 channels x [hi 32 | lo 32] halfs, swizzled)
-  const float* wsum;              // [768] fp32 column sums of the folded QKV weight
   const float* rot;               // [F][16][2] cos/sin per frame
   const float* table;             // [8][kTtcTable] bias * log2(e) where |rel| <= band, -1e30 elsewhere
   int band;

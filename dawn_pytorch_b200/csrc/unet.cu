@@ -847,7 +847,7 @@ int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const st
     TemporalTcArgs a{};
     a.x = xe.p; a.ldx = xe.ld; a.res = x.p; a.ldr = x.ld; a.out = dst.p; a.ldo = dst.ld;
     a.F = Fe; a.P = P; a.q_lo = hl; a.q_hi = hl + F;
-    a.Wqkv = w.tq; a.Wout = w.to; a.wsum = w.wsum; a.rot = h->ROT; a.table = h->ttc_table; a.band = h->cfg.win_width;
+    a.Wqkv = w.tq; a.Wout = w.to; a.rot = h->ROT; a.table = h->ttc_table; a.band = h->cfg.win_width;
     a.inv_wscale = w.t_inv_wscale; a.inv_oscale = w.t_inv_oscale;
     double pairs = 0;
     for (int i = hl; i < hl + F; ++i) pairs += std::min(Fe - 1, i + a.band) - std::max(0, i - a.band) + 1;

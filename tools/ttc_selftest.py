@@ -13,6 +13,8 @@ CASES = [  # F, P, band, q_lo, q_hi
     (81, 5, 40, 0, 81),
     (64, 9, 8, 0, 64),
     (180, 6, 40, 40, 140),       # shard with halos on both sides (100 owned frames)
+    (112, 300, 40, 0, 112),      # more units than SMs
+    (305, 300, 40, 40, 265),     # two segments of 112 / 113 queries
     (224, 6, 40, 0, 224),
     (240, 6, 40, 0, 240),        # the largest single window
     (240, 5, 40, 40, 240),       # edge shard: 200 owned frames + left halo
@@ -21,6 +23,8 @@ CASES = [  # F, P, band, q_lo, q_hi
     (280, 300, 40, 40, 240),     # two segments, more units than SMs
     (400, 7, 40, 0, 400),        # long single-GPU clip: three segments
     (200, 4096, 40, 0, 200),     # the bench shape of one level-0 layer
+    (280, 4096, 40, 40, 240),    # interior shard of a long clip: 2 x 100-query segments per pixel
+    (40, 4096, 40, 0, 40),       # short clip
 ]
 
 
@@ -49,6 +53,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         one(tuple(int(a) for a in sys.argv[1:]))
     else:
+        # page the image in first (the first import on a fresh box can take a minute): the per-case time boxes below are for kernels
+        subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, '.'); import torch, dawn_pytorch_b200; torch.zeros(1, device='cuda')"],
+                       timeout=400)
         for c in CASES:
             try:
                 r = subprocess.run([sys.executable, __file__, *map(str, c)], timeout=60, capture_output=True, text=True)
