@@ -77,27 +77,52 @@ __device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, 
 // instead of 64-bit descriptors halves the issuer's (uniform-)register pressure.
 constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+// The issuer warps run their control flow WARP-UNIFORMLY -- all 32 lanes wait on the barriers and compute the operands -- and elect one
+// lane per instruction (always the same lane: it also executes the commits that track its MMAs).  With provably uniform operands the
+// descriptors live in uniform registers and an MMA costs one UTCHMMA; issued from inside an `if (lane == 0)` region every operand went
+// through a per-lane R2UR loop (~75 cycles of issue per MMA, against 16 cycles of tensor-pipe time for a 128 x 32 x 16 MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t r;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t"
+      "}" : "=r"(r));
+  return r != 0;
+}
 __device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
-      ".reg .pred p;\n\t"
+      ".reg .pred p, q;\n\t"
       ".reg .b64 da, db;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "mov.b64 da, {%1, %5};\n\t"
       "mov.b64 db, {%2, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
       "}" ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
       : "memory");
 }
 __device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t blo, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
-      ".reg .pred p;\n\t"
+      ".reg .pred p, q;\n\t"
       ".reg .b64 db;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "mov.b64 db, {%2, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t"
       "}" ::"r"(tmem_d), "r"(tmem_a), "r"(blo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+      : "memory");
+}
+__device__ __forceinline__ void commit_elected(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(smem_u32(bar))
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
@@ -163,7 +188,8 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
   __shared__ uint32_t s_tmem_base;
   // round up inside the shared window (pointer arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform by construction (the issuer warps rely on it)
 
   if (tid == 0) {
     mbar_init(&bars.x_ready, 256); mbar_init(&bars.kv_ready, 256); mbar_init(&bars.v_ready, 256);
@@ -517,10 +543,12 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;" ::: "memory");
   }
   if (warp == MMA_WARP || warp == MMA_WARP + 1) {
-    // ======================================================================= MMA issuers: warp 8 lane 0 -> tile 0 (+ weight images), warp 9 lane 0 -> tile 1
-    if (lane == 0) {
+    // ======================================================================= MMA issuers: warp 8 -> tile 0 (+ weight images), warp 9 -> tile 1
+    // (whole warps, warp-uniform control flow; one elected lane per MMA / commit / copy: see mma_ss)
+    {
       const int j = warp - MMA_WARP;
       const uint32_t sb = smem_u32(smem);
+      const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);      // read from shared memory: make it a provably uniform value
       uint32_t it = 0, ui = 0, nqj = 0;
       const bool tr = TRACE && (a.trace != nullptr) && blockIdx.x == 0;
       long long tc_[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0;
@@ -532,14 +560,20 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
       auto load_wq = [&](uint32_t itn) {
         if (j != 0 || itn >= total_it) return;
         mbar_wait(&bars.wq_free, (itn & 1) ^ 1);
-        mbar_arrive_expect_tx(&bars.wq_ready, WQ_BYTES);
-        bulk_copy_g2s(smem + WQ_OFF, a.Wqkv + (size_t)(itn & 7) * WQ_BYTES, WQ_BYTES, &bars.wq_ready);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bars.wq_ready, WQ_BYTES);
+          bulk_copy_g2s(smem + WQ_OFF, a.Wqkv + (size_t)(itn & 7) * WQ_BYTES, WQ_BYTES, &bars.wq_ready);
+        }
+        __syncwarp();
       };
       auto load_wo = [&](uint32_t itn) {
         if (j != 0 || itn >= total_it) return;
         mbar_wait(&bars.wo_free, (itn & 1) ^ 1);
-        mbar_arrive_expect_tx(&bars.wo_ready, WO_BYTES);
-        bulk_copy_g2s(smem + WO_OFF, a.Wout + (size_t)(itn & 7) * WO_BYTES, WO_BYTES, &bars.wo_ready);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bars.wo_ready, WO_BYTES);
+          bulk_copy_g2s(smem + WO_OFF, a.Wout + (size_t)(itn & 7) * WO_BYTES, WO_BYTES, &bars.wo_ready);
+        }
+        __syncwarp();
       };
       load_wq(0); load_wo(0);
       for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ui) {
@@ -557,7 +591,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
         const uint32_t w_hi = desc_lo(sb + WQ_OFF), w_lo = desc_lo(sb + WQ_OFF + 96 * 128);
         const uint32_t qd = desc_lo(sb + Q_OFF + ro), kd = desc_lo(sb + K_OFF + ko);
         const uint32_t od = desc_lo(sb + O_OFF + ro), wd = desc_lo(sb + WO_OFF);
-        const uint32_t d_s = tmem_base + s_col(j), d_o = tmem_base + o_col(j), d_y = tmem_base + y_col(j);
+        const uint32_t d_s = tmem_base_u + s_col(j), d_o = tmem_base_u + o_col(j), d_y = tmem_base_u + y_col(j);
 
         auto issue_proj = [&](uint32_t itn) {
           mbar_wait(&bars.wq_ready, itn & 1);
@@ -571,9 +605,9 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
               mma_ss(d_s, x_hi + o, w_lo + o, ID96, 1u);
               mma_ss(d_s, x_hi + o, w_hi + o, ID96, 1u);
             }
-            tc_commit(&bars.proj_ready[j]);
+            commit_elected(&bars.proj_ready[j]);
           }
-          tc_commit(&bars.wq_free);
+          commit_elected(&bars.wq_free);
           TTC_T(2);
         };
 
@@ -597,15 +631,15 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
               mma_ss(d_s, qd + hi, kd + lo, ID160, 1u);
               mma_ss(d_s, qd + hi, kd + hi, ID160, 1u);
             }
-            tc_commit(&bars.s_ready[j]);
+            commit_elected(&bars.s_ready[j]);
             TTC_T(4);
             mbar_wait(&bars.p_ready[j], nqj & 1);
             mbar_wait(&bars.v_ready, it & 1);
             TTC_T(5);
             fence_proxy_async();
             tc_fence_after();
-            // a rolled loop on purpose: unrolled, the operand descriptors of all ten steps are precomputed, and the issuer (88 registers)
-            // spends longer shuffling them than the tensor pipe needs for the MMAs
+            // a rolled loop on purpose: unrolled, the operand descriptors of all ten steps are precomputed and shuffled around for longer
+            // than the tensor pipe needs for the MMAs
 #pragma unroll 1
             for (int s = 0; s < nks; ++s) {
               // keys kb + 16 s ..: chunk (kb + 16 s) >> 6, 32-byte step inside the chunk
@@ -616,7 +650,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
               mma_ts(d_o, d_s + 8 * s, vl, ID32, 1u);
               mma_ts(d_o, d_s + 8 * s, vh, ID32, 1u);
             }
-            tc_commit(&bars.o_ready[j]);
+            commit_elected(&bars.o_ready[j]);
             TTC_T(7);
           }
           // next head's projection goes in behind P*V (its accumulator aliases the P columns); E3 / Y of this head overlap it
@@ -635,15 +669,15 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
               mma_ss(d_y, od + hi, wd + lo, ID64, 1u);
               mma_ss(d_y, od + hi, wd + hi, ID64, 1u);
             }
-            if (h == 7) tc_commit(&bars.y_ready[j]);
+            if (h == 7) commit_elected(&bars.y_ready[j]);
             ++nqj;
             TTC_T(11);
           }
-          tc_commit(&bars.wo_free);
+          commit_elected(&bars.wo_free);
           load_wo(it + 1);
         }
       }
-      if (tr && j == 0) {
+      if (tr && j == 0 && lane == 0) {
         for (int i = 0; i < 12; ++i) a.trace[32 + i] = (unsigned long long)tc_[i];
         a.trace[44] = (unsigned long long)(clock64() - t_begin); a.trace[45] = it;
       }
