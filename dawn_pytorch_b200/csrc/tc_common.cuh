@@ -58,6 +58,39 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Elected-lane forms for an issuer WARP that runs its control flow warp-uniformly (all 32 lanes wait on the barriers and compute the
+// operands; one lane -- always the same one, so the commits track its MMAs -- executes the instruction).  With provably uniform operands
+// the descriptors stay in uniform registers and an MMA costs one UTCHMMA; issued from inside an `if (lane == 0)` region every operand
+// goes through a per-lane R2UR loop (~75 cycles of issue per MMA, more than the tensor pipe needs for a 128 x 64 x 16 MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t r;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t"
+      "}" : "=r"(r));
+  return r != 0;
+}
+__device__ __forceinline__ void tc_mma_f16_elected(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_elected(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(

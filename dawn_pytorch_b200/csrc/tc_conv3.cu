@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
   __shared__ float s_stat[NWG][16];
   __shared__ __align__(16) float s_bias[NWG][64];       // bias of this epilogue warpgroup's 64 columns (single n-tile: constant for the whole launch)
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform by construction (the MMA warp relies on it)
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + C::A_BYTES;
@@ -193,8 +194,10 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
       }
     }
   } else if (warp == MMA_WARP) {
-    // =============================================================== MMA issuer
-    if (lane == 0) {
+    // =============================================================== MMA issuer: the whole warp, warp-uniform control flow, one elected
+    // lane per MMA / commit (tc_common.cuh: elect_one)
+    {
+      const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);      // read from shared memory: make it a provably uniform value
       const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t idesc2 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       constexpr uint64_t SBO_HALO = (uint64_t)(HW * 128 / 16);   // 10 pixel rows of 128 B between 8-row groups
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
               mbar_wait(&acc_free[buf], ((cg >> 1) & 1) ^ 1);
               if (tr) { const long long t1 = clock64(); t_acc += t1 - t0; t0 = t1; }
               tc_fence_after();
-              d = tmem_base + buf * ACC_COLS;
+              d = tmem_base_u + buf * ACC_COLS;
             }
             const int sb = bit % B_STAGES;
             if (tr) t0 = clock64();
@@ -241,22 +244,22 @@ __global__ void __launch_bounds__(CCfg<BN>::NTHREADS, 1) tc_conv3_kernel(const G
               const uint64_t o = (uint64_t)(j * 2);
               if (BN == 64) {
                 // the lo panel follows the hi panel in the stage: rows 64..127 of one N=128 operand
-                tc_mma_f16(d, ahi + o, bhi + o, idesc2, (in_group == 0 && j == 0) ? 0u : 1u);
-                tc_mma_f16(d, alo + o, bhi + o, idesc, 1u);
+                tc_mma_f16_elected(d, ahi + o, bhi + o, idesc2, (in_group == 0 && j == 0) ? 0u : 1u);
+                tc_mma_f16_elected(d, alo + o, bhi + o, idesc, 1u);
               } else {
-                tc_mma_f16(d, alo + o, bhi + o, idesc, (in_group == 0 && j == 0) ? 0u : 1u);
-                tc_mma_f16(d, ahi + o, blo + o, idesc, 1u);
-                tc_mma_f16(d, ahi + o, bhi + o, idesc, 1u);
+                tc_mma_f16_elected(d, alo + o, bhi + o, idesc, (in_group == 0 && j == 0) ? 0u : 1u);
+                tc_mma_f16_elected(d, ahi + o, blo + o, idesc, 1u);
+                tc_mma_f16_elected(d, ahi + o, bhi + o, idesc, 1u);
               }
             }
-            tc_commit(&b_free[sb]);
-            if (++in_group == dt) { tc_commit(&acc_full[buf]); ++cg; in_group = 0; }
+            tc_commit_elected(&b_free[sb]);
+            if (++in_group == dt) { tc_commit_elected(&acc_full[buf]); ++cg; in_group = 0; }
             if (tr) t_issue += clock64() - t0;
           }
-          tc_commit(&a_free[sa]);
+          tc_commit_elected(&a_free[sa]);
         }
       }
-      if (tr) {
+      if (tr && lane == 0) {
         p.trace[0] = (unsigned long long)(clock64() - t_begin); p.trace[1] = ntiles_done;
         p.trace[2] = (unsigned long long)t_acc; p.trace[3] = (unsigned long long)t_a;
         p.trace[4] = (unsigned long long)t_b; p.trace[5] = (unsigned long long)t_issue;

@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
   __shared__ float s_stat[NWG][16];
   __shared__ __align__(16) float s_biasv[1024];  // the whole bias vector, fetched once per CTA (the per-tile __ldg round trip was 1-3k cycles of an epilogue-bound tile)
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform by construction (the MMA warp relies on it)
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 
   if (tid == 0) {
@@ -283,8 +284,10 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
       if (p.trace != nullptr && blockIdx.x == 0) p.trace[8] = (unsigned long long)tl_wait;
     }
   } else if (warp == MMA_WARP) {
-    // =============================================================== MMA issuer
-    if (lane == 0) {
+    // =============================================================== MMA issuer: the whole warp, warp-uniform control flow, one elected
+    // lane per MMA / commit (tc_common.cuh: elect_one)
+    {
+      const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);      // read from shared memory: make it a provably uniform value
       const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // D f32, A/B f16, K-major
       const int CH = (p.drain > 0 && p.drain < CHUNK) ? p.drain : CHUNK;
       uint32_t it = 0, cg = 0;
@@ -312,20 +315,20 @@ __global__ void __launch_bounds__(Cfg<BN>::NTHREADS, 1) tc_gemm_kernel(const Gem
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint64_t ahi = make_desc(sa), alo = make_desc(sa + A_PANEL);
           const uint64_t bhi = make_desc(sa + 2 * A_PANEL), blo = make_desc(sa + 2 * A_PANEL + B_PANEL);
-          const uint32_t d = tmem_base + buf * BN;
+          const uint32_t d = tmem_base_u + buf * BN;
 #pragma unroll
           for (int j = 0; j < BKP / 16; ++j) {
             const uint64_t o = (uint64_t)(j * 2);               // +32 bytes per k-step, in 16-byte units
-            tc_mma_f16(d, alo + o, bhi + o, idesc, (chunk_first && j == 0) ? 0u : 1u);
-            tc_mma_f16(d, ahi + o, blo + o, idesc, 1u);
-            tc_mma_f16(d, ahi + o, bhi + o, idesc, 1u);
+            tc_mma_f16_elected(d, alo + o, bhi + o, idesc, (chunk_first && j == 0) ? 0u : 1u);
+            tc_mma_f16_elected(d, ahi + o, blo + o, idesc, 1u);
+            tc_mma_f16_elected(d, ahi + o, bhi + o, idesc, 1u);
           }
-          tc_commit(&slot_free[s]);
-          if (chunk_last) { tc_commit(&acc_full[buf]); ++cg; }
+          tc_commit_elected(&slot_free[s]);
+          if (chunk_last) { tc_commit_elected(&acc_full[buf]); ++cg; }
           if (tr) t_issue += clock64() - t0;
         }
       }
-      if (tr) {
+      if (tr && lane == 0) {
         p.trace[0] = (unsigned long long)(clock64() - t_begin); p.trace[1] = it;
         p.trace[2] = (unsigned long long)t_acc; p.trace[3] = (unsigned long long)t_a;
         p.trace[4] = (unsigned long long)t_b; p.trace[5] = (unsigned long long)t_issue;

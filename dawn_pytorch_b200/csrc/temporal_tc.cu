@@ -78,19 +78,9 @@ __device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, 
 constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
 // The issuer warps run their control flow WARP-UNIFORMLY -- all 32 lanes wait on the barriers and compute the operands -- and elect one
-// lane per instruction (always the same lane: it also executes the commits that track its MMAs).  With provably uniform operands the
+// lane per instruction (always the same lane: it also executes the commits that track its MMAs; tc_common.cuh: elect_one).  With provably uniform operands the
 // descriptors live in uniform registers and an MMA costs one UTCHMMA; issued from inside an `if (lane == 0)` region every operand went
 // through a per-lane R2UR loop (~75 cycles of issue per MMA, against 16 cycles of tensor-pipe time for a 128 x 32 x 16 MMA).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t r;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, q;\n\t"
-      "}" : "=r"(r));
-  return r != 0;
-}
 __device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -114,15 +104,6 @@ __device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_
       "mov.b64 db, {%2, %5};\n\t"
       "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t"
       "}" ::"r"(tmem_d), "r"(tmem_a), "r"(blo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
-      : "memory");
-}
-__device__ __forceinline__ void commit_elected(uint64_t* bar) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
-      "}" ::"r"(smem_u32(bar))
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
@@ -605,9 +586,9 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
               mma_ss(d_s, x_hi + o, w_lo + o, ID96, 1u);
               mma_ss(d_s, x_hi + o, w_hi + o, ID96, 1u);
             }
-            commit_elected(&bars.proj_ready[j]);
+            tc_commit_elected(&bars.proj_ready[j]);
           }
-          commit_elected(&bars.wq_free);
+          tc_commit_elected(&bars.wq_free);
           TTC_T(2);
         };
 
@@ -631,7 +612,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
               mma_ss(d_s, qd + hi, kd + lo, ID160, 1u);
               mma_ss(d_s, qd + hi, kd + hi, ID160, 1u);
             }
-            commit_elected(&bars.s_ready[j]);
+            tc_commit_elected(&bars.s_ready[j]);
             TTC_T(4);
             mbar_wait(&bars.p_ready[j], nqj & 1);
             mbar_wait(&bars.v_ready, it & 1);
@@ -650,7 +631,7 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
               mma_ts(d_o, d_s + 8 * s, vl, ID32, 1u);
               mma_ts(d_o, d_s + 8 * s, vh, ID32, 1u);
             }
-            commit_elected(&bars.o_ready[j]);
+            tc_commit_elected(&bars.o_ready[j]);
             TTC_T(7);
           }
           // next head's projection goes in behind P*V (its accumulator aliases the P columns); E3 / Y of this head overlap it
@@ -669,11 +650,11 @@ __global__ void __launch_bounds__(NTH, 1) temporal_tc_kernel(const TemporalTcArg
               mma_ss(d_y, od + hi, wd + lo, ID64, 1u);
               mma_ss(d_y, od + hi, wd + hi, ID64, 1u);
             }
-            if (h == 7) commit_elected(&bars.y_ready[j]);
+            if (h == 7) tc_commit_elected(&bars.y_ready[j]);
             ++nqj;
             TTC_T(11);
           }
-          commit_elected(&bars.wo_free);
+          tc_commit_elected(&bars.wo_free);
           load_wo(it + 1);
         }
       }
