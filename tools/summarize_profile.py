@@ -78,6 +78,22 @@ def main(src, tag, title):
                "conv3x3_l0": per_launch(lambda n: "tc_conv3_kernel<64" in n, pick_max=False),      # every 64-output-channel (= level-0) 3x3 conv of the step
                "gn_apply_l0": per_launch(lambda n: "gn_apply_kernel" in n),
                "whole_step": {"dram_bytes": tot_b, "ncu_ms": tot_ns / 1e6, "launches": len(step)}}
+    raw = os.path.join(src, "full_raw.csv")
+    if os.path.exists(raw):
+        # where the --set full capture holds the kernel, its DRAM bytes replace the metrics-pass ones (the roofline contract names --set full)
+        rows = list(csv.reader(open(raw)))
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        byt = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tms = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+        cr = [i for i, h in enumerate(hdr) if h.endswith("dram__bytes_read.sum")][0]
+        cw = [i for i, h in enumerate(hdr) if h.endswith("dram__bytes_write.sum")][0]
+        cd = [i for i, h in enumerate(hdr) if h.endswith("gpu__time_duration.sum")][0]
+        for cat, pat in (("temporal_fused_l0", "temporal_tc_kernel"), ("conv3x3_l0", "tc_conv3_kernel<64"), ("gn_apply_l0", "gn_apply_kernel")):
+            xs = [r for r in data if pat in r[4]]
+            if xs:
+                traffic[cat] = {"dram_bytes_per_launch": sum(float(r[cr]) * byt[units[cr]] + float(r[cw]) * byt[units[cw]] for r in xs) / len(xs),
+                                "launches_captured": len(xs), "ncu_ms": sum(float(r[cd]) * tms[units[cd]] for r in xs) / len(xs),
+                                "source": "ncu --set full (" + os.path.basename(tag) + "_ncu_full_summary.md)"}
     with open(tag + "_traffic.json", "w") as f:
         json.dump(traffic, f, indent=1)
     print(open(tag + "_launch_summary.md").read()[:3000])
@@ -92,9 +108,13 @@ def main(src, tag, title):
                 ("tensor pipe (any) active %", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active"),
                 ("achieved occupancy %", "sm__warps_active.avg.pct_of_peak_sustained_active"), ("registers/thread", "launch__registers_per_thread"),
                 ("dynamic smem/block", "launch__shared_mem_per_block_dynamic"), ("issue slots busy %", "sm__inst_issued.avg.pct_of_peak_sustained_active"),
-                ("L2 hit rate %", "lts__t_sector_hit_rate.pct"), ("DRAM throughput % of peak", "dram__throughput.avg.pct_of_peak_sustained_elapsed")]
+                ("L2 hit rate %", "lts__t_sector_hit_rate.pct"),
+                ("stall long_scoreboard", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
+                ("stall barrier", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"),
+                ("stall wait", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"),
+                ("stall short_scoreboard", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio")]
         with open(tag + "_ncu_full_summary.md", "w") as f:
-            f.write(f"# {title} — `ncu --set full --clock-control none --import-source on`, {len(data)} launches (B200, 200 f x 64x64; `tools/gpu_call_final2.sh`)\n\n")
+            f.write(f"# {title} — `ncu --set full --clock-control none --import-source on`, {len(data)} launches (B200, 200 f x 64x64; `tools/gpu_call_ncufull.sh`)\n\n")
             f.write("| metric | " + " | ".join(f"launch {i}" for i in range(len(data))) + " |\n|---|" + "---:|" * len(data) + "\n")
             f.write("| kernel | " + " | ".join(short(r[4])[:44] for r in data) + " |\n")
             for label, key in want:
