@@ -830,12 +830,13 @@ int temporal_attn(Ctx& c, const AttnW& w, const Act& x, const Act& dst, const st
     DAWN_NCCL_OK(g_nccl.GroupEnd());
     xe = Act{h->XE, x.C, x.C, x.H, x.W};
   }
-  // tcgen05 kernel: one work unit per pixel while the sequence fits one 240-frame window (a 200-frame shard plus one halo).  Longer sequences
-  // are cut into segments that each pay the full two-tile cost: up to ~270 frames the mma.sync kernel, which keeps the whole sequence on
-  // chip, is faster; beyond its limit (a 200-frame shard with both halos = 280 frames) the segments win over the unfused path again.
+  // tcgen05 kernel: one work unit per pixel while the sequence fits one 240-frame window (a 200-frame shard plus one halo); longer sequences
+  // are cut into segments that each pay the full two-tile cost.  Since the issuer warps run warp-uniformly (r2-h) two segments of a
+  // 280-frame sequence (a 200-frame shard with both halos) take 3.5 ms at level 0, against ~4.3 ms for the mma.sync kernel that keeps the
+  // whole sequence on chip: the tcgen05 kernel is used whenever it supports the shape (DAWN_TA_TC=0 selects the older kernels).
   const bool ttc_ok = h->use_ta_tc && w.tq && h->ttc_table && temporal_tc_supported(x.C, Fe, h->cfg.win_width, hl, hl + F);
   const bool fused_ok = h->use_fused_ta && w.fq && temporal_fused_supported(x.C, Fe, h->cfg.win_width, hl, hl + F);
-  if (ttc_ok && (Fe <= kTtcWindowMax || !fused_ok)) {
+  if (ttc_ok) {
     // long sequences are cut into segments whose windows overlap: an in-place layer would let one segment read rows another already
     // replaced, so the input is copied aside first (sharded runs already read from the halo-extended copy)
     if (Fe > kTtcWindowMax && xe.p == dst.p) {

@@ -341,6 +341,7 @@ def test_general_entry_selects_its_init_conv_path_on_the_device():
     ("edge_f41", 41, 16, 8, 523),       # first length at which the band excludes a pair (|i-j| = 41 > 40), h = 2w
     ("edge_f81", 81, 8, 8, 47),         # 2*window + 1: the centre frame sees the whole clip, the ends half of it
     ("edge_f17x24", 17, 24, 24, 300),   # latent side not a power of two (24 = 8*3): level sizes 24, 12, 6, 3
+    ("long_f250x8", 250, 8, 8, 640),    # > 240 frames on one GPU: two overlapping on-chip segments per pixel at level 0 (in-place layer: input copied aside)
 ])
 def test_edge_geometries_against_oracle(tag, F, h, w, t):
     """Ragged / extreme geometries the fused kernels special-case (frame counts around the +-40 window and the 16-frame MMA
