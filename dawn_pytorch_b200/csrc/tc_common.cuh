@@ -46,18 +46,6 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // Elected-lane forms for an issuer WARP that runs its control flow warp-uniformly (all 32 lanes wait on the barriers and compute the
 // operands; one lane -- always the same one, so the commits track its MMAs -- executes the instruction).  With provably uniform operands
 // the descriptors stay in uniform registers and an MMA costs one UTCHMMA; issued from inside an `if (lane == 0)` region every operand
@@ -127,9 +115,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 // descriptor for an operand whose first row sits `shift` rows (of 128 B) into a 1024-byte swizzle atom
-__device__ __forceinline__ uint64_t make_desc_shifted(uint32_t saddr_aligned, int shift) {
-  return make_desc(saddr_aligned + shift * 128) | ((uint64_t)(shift & 7) << 49);
-}
 // byte offset of 16-byte chunk c (0..7) of row r inside a swizzled panel
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
 

@@ -62,16 +62,7 @@ __device__ __forceinline__ constexpr uint32_t y_col(int j) { return 384u + 64u *
 
 constexpr uint32_t idesc_n(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }   // D f32, A/B f16, K-major, M = 128
 
-// D[tmem] (+)= A[tmem, fp16 pairs packed per 32-bit column] * B[smem]
-__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
+// (the P*V product takes its A operand from TMEM: fp16 pairs packed per 32-bit column -- mma_ts below)
 // Every operand of this kernel is a K-major, 128-byte-swizzled panel: the descriptors differ only in their low word (start address
 // >> 4 | LBO << 16); the high word (SBO = 1024 B, descriptor version 1, SWIZZLE_128B) is one constant.  Keeping 32-bit low words
 // instead of 64-bit descriptors halves the issuer's (uniform-)register pressure.
